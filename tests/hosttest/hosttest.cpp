@@ -1,0 +1,82 @@
+// Host build (g++) of the device arithmetic headers, for CPU-side validation of the multi-limb
+// algorithms against the Python oracle.  TEST INFRASTRUCTURE: the PTX carry chains are emulated by
+// bigint.cuh's host primitives; nothing here is reachable from the product library.
+#include <stddef.h>
+#include <string.h>
+
+#include "../../plonk_b200/csrc/g1.cuh"
+
+using namespace pb;
+
+extern "C" {
+
+// op: 0 mul, 1 add, 2 sub, 3 inv(a), 4 to_mont(a), 5 from_mont(a)
+int ht_fr_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    Fr x, y, r;
+    memcpy(x.v, a + 8 * i, 32);
+    if (b) memcpy(y.v, b + 8 * i, 32);
+    switch (op) {
+      case 0: r = x * y; break;
+      case 1: r = x + y; break;
+      case 2: r = x - y; break;
+      case 3: r = x.inv(); break;
+      case 4: r = x.to_mont(); break;
+      case 5: r = x.from_mont(); break;
+      default: return -1;
+    }
+    memcpy(out + 8 * i, r.v, 32);
+  }
+  return 0;
+}
+
+int ht_fp_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    Fp x, y, r;
+    memcpy(x.v, a + 12 * i, 48);
+    if (b) memcpy(y.v, b + 12 * i, 48);
+    switch (op) {
+      case 0: r = x * y; break;
+      case 1: r = x + y; break;
+      case 2: r = x - y; break;
+      case 3: r = x.inv(); break;
+      case 4: r = x.to_mont(); break;
+      case 5: r = x.from_mont(); break;
+      default: return -1;
+    }
+    memcpy(out + 12 * i, r.v, 48);
+  }
+  return 0;
+}
+
+// Sum of n affine points (raw 96-byte layout) through xyzz_madd, with signs (1 = negate);
+// then chain-adds the partial sums pairwise through xyzz_add to also exercise the full adder.
+int ht_g1_sum(const uint32_t* pts, const uint8_t* neg, size_t n, uint32_t* out_affine) {
+  G1Xyzz acc0 = G1Xyzz::identity(), acc1 = G1Xyzz::identity();
+  for (size_t i = 0; i < n; i++) {
+    G1Affine p;
+    memcpy(&p, pts + 24 * i, 96);
+    if (p.is_inf()) continue;
+    Fp y = (neg && neg[i]) ? p.y.neg() : p.y;
+    xyzz_madd((i & 1) ? acc1 : acc0, p.x, y);
+  }
+  xyzz_add(acc0, acc1);
+  G1Affine r = xyzz_to_affine(acc0);
+  memcpy(out_affine, &r, 96);
+  return 0;
+}
+
+// k * P by double-and-add over XYZZ (exercises xyzz_dbl and xyzz_add).
+int ht_g1_mul_small(const uint32_t* pt, uint64_t k, uint32_t* out_affine) {
+  G1Affine p;
+  memcpy(&p, pt, 96);
+  G1Xyzz base = G1Xyzz::from_affine(p), acc = G1Xyzz::identity();
+  for (int bit = 63; bit >= 0; bit--) {
+    acc = xyzz_dbl(acc);
+    if ((k >> bit) & 1) xyzz_add(acc, base);
+  }
+  G1Affine r = xyzz_to_affine(acc);
+  memcpy(out_affine, &r, 96);
+  return 0;
+}
+}
