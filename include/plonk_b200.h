@@ -1,0 +1,106 @@
+/* plonk_b200 - C ABI of the B200-native backend for the dusk-plonk prover hot path.
+ *
+ * Each entry point replaces one crate-private function of the reference (paths relative to the
+ * dusk-network/plonk checkout):
+ *
+ *   pb200_ntt / pb200_ntt_dev        EvaluationDomain::{fft, ifft, coset_fft, coset_ifft}
+ *                                    src/fft/domain.rs:166-232  (best_fft :383-422)
+ *   pb200_msm_g1 / pb200_msm_g1_dev  CommitKey::commit -> msm_variable_base + Commitment::from
+ *                                    src/commitment_scheme/kzg10/key.rs:376-388,
+ *                                    src/commitment_scheme/kzg10/commitment.rs:89-93
+ *   pb200_srs_upload                 CommitKey { powers_of_g } made resident in HBM once per Prover
+ *                                    src/commitment_scheme/kzg10/key.rs:36-41
+ *   pb200_g1_compress                G1Affine::to_bytes as used by Commitment::to_bytes
+ *                                    src/commitment_scheme/kzg10/commitment.rs:95-101
+ *   pb200_prover_* / pb200_prove     Prover::new / Prover::prove (PlonkVersion::V3)
+ *                                    src/compiler/prover.rs:53-115, 415-761
+ *
+ * Data layout (identical to the reference's in-memory layout):
+ *   Fr  (BlsScalar)  4 x u64 little-endian limbs, Montgomery form R = 2^256        -> 32 bytes
+ *   G1 affine        x then y, each 6 x u64 little-endian limbs, Montgomery R=2^384 -> 96 bytes;
+ *                    the identity is encoded as x = y = 0.
+ *
+ * All functions return 0 on success or a negative pb200_status.  There is no CPU fallback: if no
+ * CUDA device is usable every call fails with PB200_ERR_CUDA (the Rust shim turns that into a
+ * panic, because the reference's Error enum has no device variant and the NTT functions are
+ * infallible - src/error.rs:21-120, src/fft/domain.rs:394).
+ * All entry points are thread safe; host-pointer variants are synchronous, *_dev variants enqueue
+ * on the given CUDA stream (a cudaStream_t passed as void*, NULL = the calling thread's default
+ * pb200 stream) and return without synchronising.
+ */
+#ifndef PLONK_B200_H
+#define PLONK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  PB200_OK = 0,
+  PB200_ERR_CUDA = -1,            /* CUDA runtime failure (no device, OOM, launch error) */
+  PB200_ERR_INVALID_DOMAIN = -2,  /* log_n >= 32: Error::InvalidEvalDomainSize (domain.rs:132-137) */
+  PB200_ERR_DEGREE_TOO_LARGE = -3,/* Error::PolynomialDegreeTooLarge (key.rs:362-370) */
+  PB200_ERR_INVALID_ARG = -4,
+  PB200_ERR_UNSATISFIED = -5,     /* Error::CircuitUnsatisfied (quotient_poly.rs:132-134) */
+  PB200_ERR_NOT_READY = -6
+} pb200_status;
+
+typedef struct pb200_srs pb200_srs_t;
+typedef struct pb200_prover pb200_prover_t;
+
+/* ---- process / device ------------------------------------------------------------------- */
+int pb200_init(int device);                 /* idempotent; selects the device for this process */
+const char* pb200_last_error(void);         /* thread-local description of the last failure */
+int pb200_device_sync(void);
+/* Number of kernels launched by this library since process start (for bench.py's gpu_launches). */
+uint64_t pb200_launch_count(void);
+
+/* ---- NTT -------------------------------------------------------------------------------- */
+/* `batch` vectors; vector b reads in + b*in_stride (in_len elements, zero padded / truncated to
+ * n = 2^log_n exactly as Vec::resize does at domain.rs:174) and writes n elements at
+ * out + b*out_stride.  inverse: 0 = fft, 1 = ifft (includes the 1/n scaling, domain.rs:187-196).
+ * coset: 0 = plain, 1 = coset variant (distribute_powers with GENERATOR = 7 before a forward
+ * transform, with 7^-1 after an inverse one; domain.rs:198-232).  Strides are in elements. */
+int pb200_ntt(const uint64_t* in, size_t in_len, uint64_t* out, uint32_t log_n, int inverse,
+              int coset, uint32_t batch, size_t in_stride, size_t out_stride);
+int pb200_ntt_dev(const uint64_t* d_in, size_t in_len, uint64_t* d_out, uint32_t log_n,
+                  int inverse, int coset, uint32_t batch, size_t in_stride, size_t out_stride,
+                  void* stream);
+
+/* ---- KZG commit key + MSM ---------------------------------------------------------------- */
+/* raw_points: n_points x 96 bytes (layout above) = CommitKey::powers_of_g. */
+int pb200_srs_upload(const uint8_t* raw_points, size_t n_points, pb200_srs_t** out);
+void pb200_srs_free(pb200_srs_t* srs);
+size_t pb200_srs_len(const pb200_srs_t* srs);
+
+/* batch commitments sum_i scalars[b][i] * powers_of_g[i], i < n_scalars (n_scalars may be smaller
+ * than the key: zip semantics of msm_variable_base).  n_scalars > pb200_srs_len() returns
+ * PB200_ERR_DEGREE_TOO_LARGE.  out_affine: batch x 96 bytes, normalised affine points. */
+int pb200_msm_g1(const pb200_srs_t* srs, const uint64_t* scalars, size_t n_scalars, uint32_t batch,
+                 size_t stride, uint64_t* out_affine);
+int pb200_msm_g1_dev(const pb200_srs_t* srs, const uint64_t* d_scalars, size_t n_scalars,
+                     uint32_t batch, size_t stride, uint64_t* out_affine_host, void* stream);
+/* Partial MSM over the point range [first, first + n_scalars) of the key, for sharding one large
+ * MSM across GPUs by points; the caller adds the per-rank results. */
+int pb200_msm_g1_range(const pb200_srs_t* srs, size_t first, const uint64_t* scalars,
+                       size_t n_scalars, uint64_t* out_affine);
+
+/* 48-byte compressed encoding of one affine point given in the 96-byte raw layout. */
+int pb200_g1_compress(const uint64_t* affine_raw, uint8_t out48[48]);
+/* out = a + b for two points in the 96-byte raw layout (host-side helper for multi-GPU reduction). */
+int pb200_g1_add_affine(const uint64_t* a_raw, const uint64_t* b_raw, uint64_t* out_raw);
+
+/* ---- measurement helpers ----------------------------------------------------------------- */
+/* Register-only IMAD.WIDE microbenchmark: returns achieved 32x32+64 multiply-adds per second. */
+int pb200_imad_peak(double* mads_per_sec);
+/* Elementwise Fr / Fp Montgomery products on the device (kernel self-test of the arithmetic). */
+int pb200_selftest_fr_mul(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
+int pb200_selftest_fp_mul(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLONK_B200_H */

@@ -1,0 +1,72 @@
+"""ctypes loader for libplonk_b200.so (the C ABI declared in include/plonk_b200.h).
+
+Fails loudly when the CUDA library is missing: there is no CPU fallback in the product path."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libplonk_b200.so")
+
+PB200_OK = 0
+PB200_ERR_CUDA = -1
+PB200_ERR_INVALID_DOMAIN = -2
+PB200_ERR_DEGREE_TOO_LARGE = -3
+PB200_ERR_INVALID_ARG = -4
+PB200_ERR_UNSATISFIED = -5
+
+_lib = None
+
+# every symbol include/plonk_b200.h declares (tests/test_abi.py checks the list against the header)
+EXPORTS = [
+    "pb200_init", "pb200_last_error", "pb200_device_sync", "pb200_launch_count",
+    "pb200_ntt", "pb200_ntt_dev",
+    "pb200_srs_upload", "pb200_srs_free", "pb200_srs_len",
+    "pb200_msm_g1", "pb200_msm_g1_dev", "pb200_msm_g1_range",
+    "pb200_g1_compress", "pb200_g1_add_affine",
+    "pb200_imad_peak", "pb200_selftest_fr_mul", "pb200_selftest_fp_mul",
+]
+
+
+class Pb200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"plonk_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with ./build.sh (or __graft_entry__.build()); "
+                "plonk_b200 has no CPU fallback"
+            )
+        L = ctypes.CDLL(LIB_PATH)
+        c = ctypes
+        L.pb200_last_error.restype = c.c_char_p
+        L.pb200_launch_count.restype = c.c_uint64
+        L.pb200_srs_len.restype = c.c_size_t
+        L.pb200_srs_len.argtypes = [c.c_void_p]
+        L.pb200_srs_free.argtypes = [c.c_void_p]
+        L.pb200_srs_free.restype = None
+        L.pb200_init.argtypes = [c.c_int]
+        L.pb200_ntt.argtypes = [c.c_void_p, c.c_size_t, c.c_void_p, c.c_uint32, c.c_int, c.c_int, c.c_uint32, c.c_size_t, c.c_size_t]
+        L.pb200_ntt_dev.argtypes = L.pb200_ntt.argtypes + [c.c_void_p]
+        L.pb200_srs_upload.argtypes = [c.c_void_p, c.c_size_t, c.POINTER(c.c_void_p)]
+        L.pb200_msm_g1.argtypes = [c.c_void_p, c.c_void_p, c.c_size_t, c.c_uint32, c.c_size_t, c.c_void_p]
+        L.pb200_msm_g1_dev.argtypes = L.pb200_msm_g1.argtypes + [c.c_void_p]
+        L.pb200_msm_g1_range.argtypes = [c.c_void_p, c.c_size_t, c.c_void_p, c.c_size_t, c.c_void_p]
+        L.pb200_g1_compress.argtypes = [c.c_void_p, c.c_void_p]
+        L.pb200_g1_add_affine.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p]
+        L.pb200_imad_peak.argtypes = [c.POINTER(c.c_double)]
+        L.pb200_selftest_fr_mul.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_size_t]
+        L.pb200_selftest_fp_mul.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_size_t]
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise Pb200Error(rc, lib().pb200_last_error().decode())

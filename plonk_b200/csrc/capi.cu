@@ -1,0 +1,199 @@
+// extern "C" surface of libplonk_b200 (see include/plonk_b200.h for the reference call sites each
+// entry point replaces).  Host-pointer variants stage through stream-ordered device allocations;
+// there is no CPU fallback anywhere: without a usable CUDA device every call returns PB200_ERR_CUDA.
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "host_field.h"
+
+struct pb200_srs;
+
+namespace pb {
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{0};
+
+static std::mutex g_init_mu;
+static int g_device = -1;
+
+int ensure_init() {
+  std::lock_guard<std::mutex> lk(g_init_mu);
+  if (g_device >= 0) {
+    PB_CUDA(cudaSetDevice(g_device));
+    return 0;
+  }
+  int count = 0;
+  PB_CUDA(cudaGetDeviceCount(&count));
+  if (count == 0) return fail(PB200_ERR_CUDA, "no CUDA device");
+  int dev = 0;
+  PB_CUDA(cudaGetDevice(&dev));
+  g_device = dev;
+  return 0;
+}
+
+cudaStream_t thread_stream() {
+  static thread_local cudaStream_t st = nullptr;
+  if (!st) {
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) st = nullptr;
+  }
+  return st;
+}
+
+int ntt_run(const uint64_t* d_in, size_t in_len, uint64_t* d_out, uint32_t log_n, int inverse, int coset,
+            uint32_t batch, size_t in_stride, size_t out_stride, cudaStream_t st);
+int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_t n, uint32_t batch,
+            size_t stride, uint64_t* out_affine_host, cudaStream_t st);
+int srs_upload(const uint8_t* raw, size_t n_points, pb200_srs** out);
+int selftest_mul(int which, const uint64_t* a, const uint64_t* b, uint64_t* o, size_t n);
+int imad_peak(double* out);
+size_t srs_len(const pb200_srs* s);
+void srs_free(pb200_srs* s);
+}  // namespace pb
+
+using namespace pb;
+
+extern "C" {
+
+int pb200_init(int device) {
+  {
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    int count = 0;
+    PB_CUDA(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(PB200_ERR_CUDA, "no such CUDA device");
+    PB_CUDA(cudaSetDevice(device));
+    g_device = device;
+  }
+  // raise the stream-ordered pool's release threshold so per-call workspaces are recycled
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  return 0;
+}
+
+const char* pb200_last_error(void) { return g_last_error.c_str(); }
+
+int pb200_device_sync(void) {
+  PB_TRY(ensure_init());
+  PB_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+
+uint64_t pb200_launch_count(void) { return g_launches.load(); }
+
+int pb200_ntt_dev(const uint64_t* d_in, size_t in_len, uint64_t* d_out, uint32_t log_n, int inverse, int coset,
+                  uint32_t batch, size_t in_stride, size_t out_stride, void* stream) {
+  PB_TRY(ensure_init());
+  cudaStream_t st = stream ? (cudaStream_t)stream : thread_stream();
+  return ntt_run(d_in, in_len, d_out, log_n, inverse, coset, batch, in_stride, out_stride, st);
+}
+
+int pb200_ntt(const uint64_t* in, size_t in_len, uint64_t* out, uint32_t log_n, int inverse, int coset,
+              uint32_t batch, size_t in_stride, size_t out_stride) {
+  PB_TRY(ensure_init());
+  if (log_n >= 32) return fail(PB200_ERR_INVALID_DOMAIN, "log_n >= TWO_ADACITY");
+  if (batch == 0) return 0;
+  if ((!in && in_len) || !out) return fail(PB200_ERR_INVALID_ARG, "null buffer");
+  cudaStream_t st = thread_stream();
+  const size_t n = (size_t)1 << log_n;
+  const size_t use = in_len < n ? in_len : n;
+  uint64_t *d_in = nullptr, *d_out = nullptr;
+  PB_CUDA(cudaMallocAsync((void**)&d_out, (size_t)batch * n * 32, st));
+  if (use) {
+    PB_CUDA(cudaMallocAsync((void**)&d_in, (size_t)batch * use * 32, st));
+    PB_CUDA(cudaMemcpy2DAsync(d_in, use * 32, in, in_stride * 32, use * 32, batch, cudaMemcpyHostToDevice, st));
+  }
+  int rc = ntt_run(d_in, use, d_out, log_n, inverse, coset, batch, use, n, st);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpy2DAsync(out, out_stride * 32, d_out, n * 32, n * 32, batch, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail(PB200_ERR_CUDA, "ntt result copy", cudaGetErrorString(e));
+  }
+  if (d_in) cudaFreeAsync(d_in, st);
+  cudaFreeAsync(d_out, st);
+  return rc;
+}
+
+int pb200_srs_upload(const uint8_t* raw_points, size_t n_points, pb200_srs_t** out) {
+  PB_TRY(ensure_init());
+  if (!raw_points || !out) return fail(PB200_ERR_INVALID_ARG, "null argument");
+  return srs_upload(raw_points, n_points, out);
+}
+void pb200_srs_free(pb200_srs_t* srs) {
+  if (srs) srs_free(srs);
+}
+size_t pb200_srs_len(const pb200_srs_t* srs) { return srs ? srs_len(srs) : 0; }
+
+int pb200_msm_g1_dev(const pb200_srs_t* srs, const uint64_t* d_scalars, size_t n_scalars, uint32_t batch,
+                     size_t stride, uint64_t* out_affine_host, void* stream) {
+  PB_TRY(ensure_init());
+  if (!srs || !out_affine_host) return fail(PB200_ERR_INVALID_ARG, "null argument");
+  cudaStream_t st = stream ? (cudaStream_t)stream : thread_stream();
+  return msm_run(srs, 0, d_scalars, n_scalars, batch, stride, out_affine_host, st);
+}
+
+static int msm_host(const pb200_srs_t* srs, size_t first, const uint64_t* scalars, size_t n, uint32_t batch,
+                    size_t stride, uint64_t* out) {
+  PB_TRY(ensure_init());
+  if (!srs || !out || (!scalars && n)) return fail(PB200_ERR_INVALID_ARG, "null argument");
+  if (first + n > srs_len(srs)) return fail(PB200_ERR_DEGREE_TOO_LARGE, "more scalars than commit-key points");
+  cudaStream_t st = thread_stream();
+  uint64_t* d = nullptr;
+  if (n && batch) {
+    PB_CUDA(cudaMallocAsync((void**)&d, (size_t)batch * n * 32, st));
+    PB_CUDA(cudaMemcpy2DAsync(d, n * 32, scalars, stride * 32, n * 32, batch, cudaMemcpyHostToDevice, st));
+  }
+  int rc = msm_run(srs, first, d, n, batch, n, out, st);
+  if (d) cudaFreeAsync(d, st);
+  return rc;
+}
+
+int pb200_msm_g1(const pb200_srs_t* srs, const uint64_t* scalars, size_t n_scalars, uint32_t batch, size_t stride,
+                 uint64_t* out_affine) {
+  return msm_host(srs, 0, scalars, n_scalars, batch, stride, out_affine);
+}
+int pb200_msm_g1_range(const pb200_srs_t* srs, size_t first, const uint64_t* scalars, size_t n_scalars,
+                       uint64_t* out_affine) {
+  return msm_host(srs, first, scalars, n_scalars, 1, n_scalars, out_affine);
+}
+
+int pb200_g1_compress(const uint64_t* affine_raw, uint8_t out48[48]) {
+  if (!affine_raw || !out48) return fail(PB200_ERR_INVALID_ARG, "null argument");
+  pbh::g1_compress_raw(affine_raw, out48);
+  return 0;
+}
+
+int pb200_g1_add_affine(const uint64_t* a_raw, const uint64_t* b_raw, uint64_t* out_raw) {
+  if (!a_raw || !b_raw || !out_raw) return fail(PB200_ERR_INVALID_ARG, "null argument");
+  auto load = [](const uint64_t* r) {
+    pbh::HXyzz p;
+    memcpy(p.x.v, r, 48);
+    memcpy(p.y.v, r + 6, 48);
+    if (p.x.is_zero() && p.y.is_zero()) return pbh::HXyzz::identity();
+    p.zz = pbh::HFp::one();
+    p.zzz = pbh::HFp::one();
+    return p;
+  };
+  pbh::HXyzz a = load(a_raw), b = load(b_raw);
+  pbh::hxyzz_add(a, b);
+  pbh::HFp x, y;
+  pbh::hxyzz_to_affine(a, &x, &y);
+  memcpy(out_raw, x.v, 48);
+  memcpy(out_raw + 6, y.v, 48);
+  return 0;
+}
+
+int pb200_imad_peak(double* mads_per_sec) {
+  PB_TRY(ensure_init());
+  return imad_peak(mads_per_sec);
+}
+int pb200_selftest_fr_mul(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  PB_TRY(ensure_init());
+  return selftest_mul(0, a, b, out, n);
+}
+int pb200_selftest_fp_mul(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  PB_TRY(ensure_init());
+  return selftest_mul(1, a, b, out, n);
+}
+}

@@ -1,0 +1,52 @@
+// Shared host-side plumbing of libplonk_b200: error reporting, per-thread streams, launch counting.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/plonk_b200.h"
+#include "bigint.cuh"
+
+namespace pb {
+
+extern thread_local std::string g_last_error;
+extern std::atomic<uint64_t> g_launches;
+
+inline int fail(int code, const char* what, const char* detail = "") {
+  g_last_error = std::string(what) + (detail[0] ? ": " : "") + detail;
+  return code;
+}
+
+#define PB_CUDA(expr)                                                                     \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      char _buf[256];                                                                     \
+      snprintf(_buf, sizeof _buf, "%s at %s:%d", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return pb::fail(PB200_ERR_CUDA, #expr, _buf);                                       \
+    }                                                                                     \
+  } while (0)
+
+#define PB_TRY(expr)          \
+  do {                        \
+    int _s = (expr);          \
+    if (_s != 0) return _s;   \
+  } while (0)
+
+// Counted kernel launch: every kernel this library runs goes through here.
+#define PB_LAUNCH(kernel, grid, block, smem, stream, ...)            \
+  do {                                                               \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);      \
+    pb::g_launches.fetch_add(1, std::memory_order_relaxed);          \
+  } while (0)
+
+// The calling thread's pb200 stream (created on first use, never destroyed).
+cudaStream_t thread_stream();
+int ensure_init();
+
+inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+}  // namespace pb

@@ -1,0 +1,372 @@
+// Radix-2 NTT / iNTT / coset variants over the BLS12-381 scalar field on sm_100a.
+//
+// Replaces EvaluationDomain::{fft, ifft, coset_fft, coset_ifft} (reference src/fft/domain.rs:166-232;
+// the reference schedule is best_fft/serial_fft :383-463: bit-reversal + log n DIT stages whose
+// twiddles are a running product).  The transform is exact field arithmetic, so any schedule that
+// computes the same DFT is bit-identical; ours is GPU-first:
+//
+//   * N = R_0 * R_1 (* R_2): one kernel launch per factor ("pass").  A pass loads a tile of T
+//     independent size-R sub-transforms into shared memory (T consecutive elements per row, so
+//     every global access is a contiguous T*32-byte segment), runs log R radix-2 DIF stages out
+//     of shared memory, multiplies by the inter-pass twiddle w_M^(k*lo) and stores in place.
+//     The last pass stores to the digit-reversed position, so input and output are both in
+//     natural order and there is no separate bit-reversal sweep.
+//   * Twiddles come from per-size tables resident in HBM (w^i, i < M/2; w^(i+M/2) = -w^i), built
+//     once per domain size; the sub-transform tables are tiny and stay in L1/L2.
+//   * Zero padding (Vec::resize, domain.rs:174), the coset pre-scale g^i (distribute_powers,
+//     domain.rs:198-204) and the 1/n and g^-i post-scales (domain.rs:187-196, 229-232) are fused
+//     into the first pass' loads and the last pass' stores.
+//   * Shared-memory layout is split in two 16-byte planes per element so that a warp reading
+//     32 consecutive elements is bank-conflict free.
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace pb {
+
+static constexpr int kMaxLogTile = 11;  // 2048 elements = 64 KiB of shared memory per CTA
+static constexpr int kNttThreads = 256;
+
+PB_D Fr ld_fr(const uint4* p, size_t i) {
+  uint4 a = __ldg(p + 2 * i), b = __ldg(p + 2 * i + 1);
+  Fr r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+PB_D Fr ld_fr_nc(const uint4* p, size_t i) {  // data that other CTAs may have written in this stream: plain load
+  uint4 a = p[2 * i], b = p[2 * i + 1];
+  Fr r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+PB_D void st_fr(uint4* p, size_t i, const Fr& r) {
+  p[2 * i] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  p[2 * i + 1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+PB_D Fr lds_fr(const uint4* s0, const uint4* s1, int i) {
+  uint4 a = s0[i], b = s1[i];
+  Fr r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+PB_D void sts_fr(uint4* s0, uint4* s1, int i, const Fr& r) {
+  s0[i] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  s1[i] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+
+struct PassArgs {
+  const uint4* in;
+  uint4* out;
+  unsigned long long in_len, in_stride, out_stride;  // elements
+  int r;         // log2 of this pass' radix R
+  int log_lo;    // log2 of the product of the later radices (0 for the last pass)
+  int log_h;     // log2 of the product of the earlier radices
+  int log_t;     // log2 of the tile width T
+  int log_r0;    // log2 of the first pass' radix (last pass only; 0 if single pass)
+  int first, last;
+  const uint4* w_r;   // w_R^i,   i < R/2
+  const uint4* w_m;   // w_M^i,   i < M/2, M = R * Lo  (not last)
+  const uint4* pre;   // first pass: element-wise pre-scale table or null
+  const uint4* post;  // last pass: element-wise post-scale table or null
+  int has_scalar;     // last pass: multiply every output by `scalar`
+  Fr scalar;
+};
+
+__global__ void __launch_bounds__(kNttThreads) k_ntt_pass(PassArgs a) {
+  extern __shared__ uint4 smem[];
+  const int tid = threadIdx.x;
+  const int R = 1 << a.r, T = 1 << a.log_t, tile = R << a.log_t;
+  uint4* S0 = smem;
+  uint4* S1 = smem + tile;
+  const uint4* in = a.in + 2 * (size_t)blockIdx.y * a.in_stride;
+  uint4* out = a.out + 2 * (size_t)blockIdx.y * a.out_stride;
+  const size_t blk = blockIdx.x;
+
+  size_t base = 0, lo0 = 0, k0b = 0, mid = 0;
+  const int log_hmid = a.log_h - a.log_r0;  // rows per first-pass digit (last pass)
+  if (!a.last) {
+    const int log_lo_tiles = a.log_lo - a.log_t;
+    const size_t h = blk >> log_lo_tiles;
+    lo0 = (blk & (((size_t)1 << log_lo_tiles) - 1)) << a.log_t;
+    base = (h << (a.r + a.log_lo)) + lo0;
+    for (int idx = tid; idx < tile; idx += kNttThreads) {
+      const int j = idx >> a.log_t, t = idx & (T - 1);
+      const size_t g = base + ((size_t)j << a.log_lo) + t;
+      Fr v;
+      if (a.first) {
+        if (g < a.in_len) {
+          v = ld_fr(in, g);
+          if (a.pre) v = v * ld_fr(a.pre, g);
+        } else {
+          v = Fr::zero();
+        }
+      } else {
+        v = ld_fr_nc(in, g);
+      }
+      sts_fr(S0, S1, idx, v);
+    }
+  } else {
+    const int log_k0_tiles = a.log_r0 - a.log_t;
+    mid = blk >> log_k0_tiles;
+    k0b = (blk & (((size_t)1 << log_k0_tiles) - 1)) << a.log_t;
+    for (int idx = tid; idx < tile; idx += kNttThreads) {
+      const int t = idx >> a.r, j = idx & (R - 1);
+      const size_t h = ((k0b + t) << log_hmid) + mid;
+      const size_t g = (h << a.r) + j;
+      Fr v;
+      if (a.first) {
+        if (g < a.in_len) {
+          v = ld_fr(in, g);
+          if (a.pre) v = v * ld_fr(a.pre, g);
+        } else {
+          v = Fr::zero();
+        }
+      } else {
+        v = ld_fr_nc(in, g);
+      }
+      sts_fr(S0, S1, (j << a.log_t) + t, v);
+    }
+  }
+  __syncthreads();
+
+  // log R radix-2 decimation-in-frequency stages: natural order in, bit-reversed order out.
+  for (int s = 0; s < a.r; s++) {
+    const int log_half = a.r - s - 1;
+    const int half = 1 << log_half;
+    for (int b = tid; b < (tile >> 1); b += kNttThreads) {
+      const int t = b & (T - 1);
+      const int jj = b >> a.log_t;
+      const int grp = jj >> log_half, pos = jj & (half - 1);
+      const int j0 = (grp << (log_half + 1)) + pos;
+      const int i0 = (j0 << a.log_t) + t;
+      const int i1 = i0 + (half << a.log_t);
+      const Fr x = lds_fr(S0, S1, i0), y = lds_fr(S0, S1, i1);
+      const Fr w = ld_fr(a.w_r, (size_t)pos << s);
+      sts_fr(S0, S1, i0, x + y);
+      sts_fr(S0, S1, i1, (x - y) * w);
+    }
+    __syncthreads();
+  }
+
+  if (!a.last) {
+    const size_t half_m = (size_t)1 << (a.r + a.log_lo - 1);
+    for (int idx = tid; idx < tile; idx += kNttThreads) {
+      const int k = idx >> a.log_t, t = idx & (T - 1);
+      const int kr = (a.r == 0) ? 0 : (int)(__brev((unsigned)k) >> (32 - a.r));
+      Fr v = lds_fr(S0, S1, (kr << a.log_t) + t);
+      const size_t e = (size_t)k * (lo0 + t);
+      Fr tw;
+      if (e < half_m) {
+        tw = ld_fr(a.w_m, e);
+      } else {
+        tw = ld_fr(a.w_m, e - half_m).neg();
+      }
+      v = v * tw;
+      st_fr(out, base + ((size_t)k << a.log_lo) + t, v);
+    }
+  } else {
+    for (int idx = tid; idx < tile; idx += kNttThreads) {
+      const int k = idx >> a.log_t, t = idx & (T - 1);
+      const int kr = (a.r == 0) ? 0 : (int)(__brev((unsigned)k) >> (32 - a.r));
+      Fr v = lds_fr(S0, S1, (kr << a.log_t) + t);
+      const size_t o = (k0b + t) + (mid << a.log_r0) + ((size_t)k << a.log_h);
+      if (a.post) v = v * ld_fr(a.post, o);
+      if (a.has_scalar) v = v * a.scalar;
+      st_fr(out, o, v);
+    }
+  }
+}
+
+// out[i] = scale * base^i, with base^(2^b) supplied by the host.
+struct PowArgs {
+  Fr p2[32];
+  Fr scale;
+};
+__global__ void k_powers(uint4* out, size_t n, PowArgs pa) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr acc = pa.scale;
+  size_t e = i;
+#pragma unroll 1
+  for (int b = 0; b < 32 && e; b++, e >>= 1)
+    if (e & 1) acc = acc * pa.p2[b];
+  st_fr(out, i, acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side: domain constants (EvaluationDomain::new, reference src/fft/domain.rs:122-158) and
+// the per-size table cache.
+// ---------------------------------------------------------------------------------------------
+static Fr fr_from_canonical(const uint32_t (&l)[8]) {
+  Fr x;
+  for (int i = 0; i < 8; i++) x.v[i] = l[i];
+  return x.to_mont();
+}
+static const uint32_t kRootOfUnity[8] = {0x439f0d2bu, 0x3829971fu, 0x8c2280b9u, 0xb6368350u,
+                                         0x22c813b4u, 0xd09b6819u, 0xdfe81f20u, 0x16a2a19eu};
+static const uint32_t kGenerator[8] = {7, 0, 0, 0, 0, 0, 0, 0};
+
+Fr ntt_group_gen(int log_n, bool inverse) {  // group_gen / group_gen_inv
+  Fr g = fr_from_canonical(kRootOfUnity);
+  for (int i = log_n; i < 32; i++) g = g.sqr();
+  return inverse ? g.inv() : g;
+}
+Fr ntt_size_inv(int log_n) {
+  uint32_t l[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  l[log_n / 32] = 1u << (log_n % 32);
+  Fr x;
+  for (int i = 0; i < 8; i++) x.v[i] = l[i];
+  return x.to_mont().inv();
+}
+Fr ntt_coset_gen(bool inverse) {
+  Fr g = fr_from_canonical(kGenerator);
+  return inverse ? g.inv() : g;
+}
+
+struct TableCache {
+  std::mutex mu;
+  uint4* w[2][33] = {};       // [inverse][log m]: w_m^(+-i), i < max(1, m/2)
+  uint4* coset_fwd = nullptr;  // g^i
+  size_t coset_fwd_len = 0;
+  uint4* coset_inv[33] = {};  // [log n]: g^-i / n
+};
+static TableCache g_tables;
+
+static int build_powers(uint4** out, size_t n, const Fr& base, const Fr& scale, cudaStream_t st) {
+  PB_CUDA(cudaMalloc((void**)out, n * 32));
+  PowArgs pa;
+  Fr p = base;
+  for (int b = 0; b < 32; b++) {
+    pa.p2[b] = p;
+    p = p.sqr();
+  }
+  pa.scale = scale;
+  PB_LAUNCH(k_powers, div_up(n, 256), 256, 0, st, *out, n, pa);
+  PB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// All table builds are issued on the caller's stream under the cache mutex; a consumer on another
+// stream must not race with the build, so we synchronise the building stream once per new table.
+static int get_twiddles(int logm, bool inverse, cudaStream_t st, const uint4** out) {
+  std::lock_guard<std::mutex> lk(g_tables.mu);
+  uint4*& slot = g_tables.w[inverse ? 1 : 0][logm];
+  if (!slot) {
+    size_t n = logm >= 1 ? ((size_t)1 << (logm - 1)) : 1;
+    PB_TRY(build_powers(&slot, n, ntt_group_gen(logm, inverse), Fr::one(), st));
+    PB_CUDA(cudaStreamSynchronize(st));
+  }
+  *out = slot;
+  return 0;
+}
+static int get_coset_fwd(size_t n, cudaStream_t st, const uint4** out) {
+  std::lock_guard<std::mutex> lk(g_tables.mu);
+  if (g_tables.coset_fwd_len < n) {
+    uint4* fresh = nullptr;
+    PB_TRY(build_powers(&fresh, n, ntt_coset_gen(false), Fr::one(), st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    // the old (shorter) table may still be in use by in-flight kernels: leak it deliberately
+    g_tables.coset_fwd = fresh;
+    g_tables.coset_fwd_len = n;
+  }
+  *out = g_tables.coset_fwd;
+  return 0;
+}
+static int get_coset_inv(int log_n, cudaStream_t st, const uint4** out) {
+  std::lock_guard<std::mutex> lk(g_tables.mu);
+  uint4*& slot = g_tables.coset_inv[log_n];
+  if (!slot) {
+    PB_TRY(build_powers(&slot, (size_t)1 << log_n, ntt_coset_gen(true), ntt_size_inv(log_n), st));
+    PB_CUDA(cudaStreamSynchronize(st));
+  }
+  *out = slot;
+  return 0;
+}
+
+static int g_ntt_plan_override[3] = {0, 0, 0};  // PB200_NTT_PLAN="r0,r1[,r2]" for tuning runs
+
+static void ntt_plan(int L, int* radices, int* n_pass) {
+  if (g_ntt_plan_override[0] && g_ntt_plan_override[0] + g_ntt_plan_override[1] + g_ntt_plan_override[2] == L) {
+    int n = 0;
+    for (int i = 0; i < 3; i++)
+      if (g_ntt_plan_override[i]) radices[n++] = g_ntt_plan_override[i];
+    *n_pass = n;
+    return;
+  }
+  if (L <= kMaxLogTile) {
+    radices[0] = L;
+    *n_pass = 1;
+  } else if (L <= 2 * kMaxLogTile - 2) {
+    radices[0] = (L + 1) / 2;
+    radices[1] = L - radices[0];
+    *n_pass = 2;
+  } else {
+    radices[0] = (L + 2) / 3;
+    radices[1] = (L - radices[0] + 1) / 2;
+    radices[2] = L - radices[0] - radices[1];
+    *n_pass = 3;
+  }
+}
+
+int ntt_run(const uint64_t* d_in, size_t in_len, uint64_t* d_out, uint32_t log_n, int inverse,
+            int coset, uint32_t batch, size_t in_stride, size_t out_stride, cudaStream_t st) {
+  if (log_n >= 32) return fail(PB200_ERR_INVALID_DOMAIN, "log_n >= TWO_ADACITY");
+  if (batch == 0) return 0;
+  static std::once_flag once;
+  static int attr_status = 0;
+  std::call_once(once, [] {
+    attr_status = (int)cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (2 << kMaxLogTile) * 16);
+    if (const char* env = getenv("PB200_NTT_PLAN"))
+      sscanf(env, "%d,%d,%d", &g_ntt_plan_override[0], &g_ntt_plan_override[1], &g_ntt_plan_override[2]);
+  });
+  if (attr_status != 0) return fail(PB200_ERR_CUDA, "cudaFuncSetAttribute(k_ntt_pass)");
+  const size_t n = (size_t)1 << log_n;
+  if (in_len > n) in_len = n;  // Vec::resize truncates (domain.rs:174)
+  int radices[3], n_pass;
+  ntt_plan((int)log_n, radices, &n_pass);
+
+  const uint4* pre = nullptr;
+  const uint4* post = nullptr;
+  if (coset && !inverse && in_len > 0) PB_TRY(get_coset_fwd(n, st, &pre));
+  if (coset && inverse) PB_TRY(get_coset_inv((int)log_n, st, &post));
+
+  int log_h = 0;
+  for (int q = 0; q < n_pass; q++) {
+    PassArgs a;
+    a.r = radices[q];
+    int log_lo = 0;
+    for (int i = q + 1; i < n_pass; i++) log_lo += radices[i];
+    a.log_lo = log_lo;
+    a.log_h = log_h;
+    a.first = (q == 0);
+    a.last = (q == n_pass - 1);
+    a.log_r0 = (n_pass > 1) ? radices[0] : 0;
+    const int room = kMaxLogTile - a.r;
+    a.log_t = a.last ? (a.log_r0 < room ? a.log_r0 : room) : (log_lo < room ? log_lo : room);
+    a.in = (const uint4*)(a.first ? d_in : d_out);
+    a.out = (uint4*)d_out;
+    a.in_len = a.first ? in_len : n;
+    a.in_stride = a.first ? in_stride : out_stride;
+    a.out_stride = out_stride;
+    PB_TRY(get_twiddles(a.r, inverse != 0, st, &a.w_r));
+    a.w_m = nullptr;
+    if (!a.last) PB_TRY(get_twiddles(a.r + log_lo, inverse != 0, st, &a.w_m));
+    a.pre = a.first ? pre : nullptr;
+    a.post = a.last ? post : nullptr;
+    a.has_scalar = (a.last && inverse && !coset) ? 1 : 0;
+    a.scalar = a.has_scalar ? ntt_size_inv((int)log_n) : Fr::zero();
+    const size_t tile = (size_t)1 << (a.r + a.log_t);
+    dim3 grid((unsigned)(n / tile), batch);
+    PB_LAUNCH(k_ntt_pass, grid, kNttThreads, tile * 32, st, a);
+    PB_CUDA(cudaGetLastError());
+    log_h += a.r;
+  }
+  return 0;
+}
+
+}  // namespace pb

@@ -1,0 +1,86 @@
+"""CommitKey / Commitment mirror (reference src/commitment_scheme/kzg10/key.rs:36-41, 362-388,
+commitment.rs:77-106) over the CUDA MSM."""
+from __future__ import annotations
+
+import ctypes
+
+from ._lib import PB200_ERR_DEGREE_TOO_LARGE, Pb200Error, check, lib
+
+G1_RAW_BYTES = 96
+FR_BYTES = 32
+
+
+class PolynomialDegreeTooLarge(ValueError):
+    """Error::PolynomialDegreeTooLarge (reference key.rs:362-370)."""
+
+
+class Commitment:
+    """Commitment(G1Affine): ``raw`` is x||y Montgomery limbs (identity = zeros)."""
+
+    def __init__(self, raw: bytes):
+        assert len(raw) == G1_RAW_BYTES
+        self.raw = raw
+
+    def to_bytes(self) -> bytes:
+        """48-byte compressed encoding (reference commitment.rs:95-101)."""
+        out = ctypes.create_string_buffer(48)
+        check(lib().pb200_g1_compress(self.raw, out))
+        return out.raw
+
+    def __eq__(self, other):
+        return isinstance(other, Commitment) and self.raw == other.raw
+
+
+class CommitKey:
+    """powers_of_g resident in HBM (uploaded once, like the immutable CommitKey of a Prover)."""
+
+    def __init__(self, raw_points: bytes):
+        assert len(raw_points) % G1_RAW_BYTES == 0 and raw_points
+        self.n_points = len(raw_points) // G1_RAW_BYTES
+        h = ctypes.c_void_p()
+        check(lib().pb200_srs_upload(raw_points, self.n_points, ctypes.byref(h)))
+        self._h = h
+
+    def max_degree(self) -> int:
+        return self.n_points - 1
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().pb200_srs_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @staticmethod
+    def _trim(poly: bytes) -> bytes:
+        """Polynomial::from_coefficients_vec drops trailing zero coefficients (polynomial.rs:79-93)."""
+        n = len(poly) // FR_BYTES
+        zero = bytes(FR_BYTES)
+        while n and poly[(n - 1) * FR_BYTES : n * FR_BYTES] == zero:
+            n -= 1
+        return poly[: n * FR_BYTES]
+
+    def commit(self, polynomial: bytes) -> Commitment:
+        return self.commit_batch([polynomial])[0]
+
+    def commit_batch(self, polynomials) -> list:
+        polys = [self._trim(p) for p in polynomials]
+        for p in polys:
+            degree = max(len(p) // FR_BYTES - 1, 0)
+            if degree > self.max_degree():
+                raise PolynomialDegreeTooLarge()
+        n = max(len(p) for p in polys) // FR_BYTES
+        stride = max(n, 1)
+        buf = bytearray(stride * FR_BYTES * len(polys))
+        for i, p in enumerate(polys):
+            buf[i * stride * FR_BYTES : i * stride * FR_BYTES + len(p)] = p
+        out = ctypes.create_string_buffer(G1_RAW_BYTES * len(polys))
+        src = (ctypes.c_char * len(buf)).from_buffer(buf)
+        try:
+            check(lib().pb200_msm_g1(self._h, src, n, len(polys), stride, out))
+        except Pb200Error as e:
+            if e.code == PB200_ERR_DEGREE_TOO_LARGE:
+                raise PolynomialDegreeTooLarge() from e
+            raise
+        return [Commitment(out.raw[i * G1_RAW_BYTES : (i + 1) * G1_RAW_BYTES]) for i in range(len(polys))]

@@ -1,0 +1,153 @@
+"""GPU parity tests (run on a B200 via gpurun): CUDA kernels behind the C ABI vs the Python oracle.
+
+Bit-exact everywhere: all arithmetic is integer/modular."""
+import ctypes
+import random
+
+import pytest
+
+from oracle import pyref as R
+from tests.util import bases_to_abi, from_abi, progression_bases, rand_fr, to_abi
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pb():
+    import plonk_b200
+    from plonk_b200._lib import check, lib
+
+    check(lib().pb200_init(0))
+    return plonk_b200
+
+
+def _edge(mod):
+    return [0, 1, 2, mod - 1, mod - 2, (mod - 1) // 2, (1 << 32) - 1, 1 << 32, (1 << 64) - 1, (1 << 255) % mod]
+
+
+@pytest.mark.parametrize("name,mod,nbytes", [("fr", R.R_MOD, 32), ("fp", R.P_MOD, 48)])
+def test_device_montgomery_mul(pb, name, mod, nbytes):
+    """The PTX carry chains as compiled by ptxas (the host test only covers the algorithm)."""
+    from plonk_b200._lib import check, lib
+
+    rng = random.Random(7)
+    vals = _edge(mod) + [rng.randrange(mod) for _ in range(4000)]
+    a = vals
+    b = [rng.choice(vals) for _ in a]
+    A = b"".join(x.to_bytes(nbytes, "little") for x in a)
+    B = b"".join(x.to_bytes(nbytes, "little") for x in b)
+    out = ctypes.create_string_buffer(len(A))
+    check(getattr(lib(), f"pb200_selftest_{name}_mul")(A, B, out, len(a)))
+    rinv = pow(1 << (8 * nbytes), -1, mod)
+    got = [int.from_bytes(out.raw[i * nbytes : (i + 1) * nbytes], "little") for i in range(len(a))]
+    assert got == [x * y * rinv % mod for x, y in zip(a, b)]
+
+
+@pytest.mark.parametrize("log_n", list(range(0, 14)))
+def test_ntt_matches_oracle_all_directions(pb, log_n):
+    rng = random.Random(1000 + log_n)
+    n = 1 << log_n
+    dom = pb.EvaluationDomain(n)
+    ref = R.EvaluationDomain(n)
+    assert dom.size == ref.size == n
+    for in_len in sorted({n, max(n // 8 + 3, 1) if n >= 8 else n, 0, n + 5}):
+        x = rand_fr(rng, in_len)
+        xb = to_abi(x)
+        assert from_abi(dom.fft(xb)) == ref.fft(x), (log_n, in_len, "fft")
+        assert from_abi(dom.ifft(xb)) == ref.ifft(x), (log_n, in_len, "ifft")
+        assert from_abi(dom.coset_fft(xb)) == ref.coset_fft(x), (log_n, in_len, "coset_fft")
+        assert from_abi(dom.coset_ifft(xb)) == ref.coset_ifft(x), (log_n, in_len, "coset_ifft")
+
+
+def test_ntt_edge_vectors_and_closed_forms(pb):
+    # reference src/fft/domain.rs:570-651
+    n = 1 << 12
+    dom, ref = pb.EvaluationDomain(n), R.EvaluationDomain(n)
+    ramp = [i + 1 for i in range(n)]  # domain.rs:574-576
+    ev = dom.fft(to_abi(ramp))
+    assert from_abi(ev) == ref.fft(ramp)
+    assert from_abi(dom.ifft(ev)) == ramp
+    for vec in ([0] * n, [1] + [0] * (n - 1), [R.R_MOD - 1] * n):
+        assert from_abi(dom.fft(to_abi(vec))) == ref.fft(vec)
+    d8 = pb.EvaluationDomain(1 << 8)
+    r8 = R.EvaluationDomain(1 << 8)
+    lin = from_abi(d8.coset_fft(to_abi([0, 1])))  # linear_coset_evaluations_match_closed_form
+    assert lin == [R.GENERATOR * pow(r8.group_gen, i, R.R_MOD) % R.R_MOD for i in range(1 << 8)]
+
+
+@pytest.mark.parametrize("log_n", [16, 19, 20])
+def test_ntt_large_properties(pb, log_n):
+    """Sizes the Python oracle cannot reach in seconds: size-independent properties + spot checks
+    of single outputs against the definition of the DFT (Horner evaluation at w^k)."""
+    rng = random.Random(log_n)
+    n = 1 << log_n
+    dom = pb.EvaluationDomain(n)
+    ref = R.EvaluationDomain(n)
+    x = rand_fr(rng, n // 8 + 3)
+    xb = to_abi(x)
+    ev = dom.coset_fft(xb)
+    back = dom.coset_ifft(ev)
+    assert back[: len(xb)] == xb and back[len(xb) :] == bytes(len(back) - len(xb))
+    evals = from_abi(ev[: 32 * 4]) + from_abi(ev[32 * (n - 1) :])
+    for k, got in zip([0, 1, 2, 3, n - 1], evals):
+        assert got == R.poly_eval(x, R.GENERATOR * pow(ref.group_gen, k, R.R_MOD) % R.R_MOD)
+    full = rand_fr(rng, 64)
+    fb = to_abi(full)
+    assert dom.ifft(dom.fft(fb))[: len(fb)] == fb
+    # batched call == individual calls
+    v2 = to_abi(rand_fr(rng, 40))
+    outs = dom.batch([xb, v2], 0, 1)
+    assert outs[0] == ev and outs[1] == dom.coset_fft(v2)
+
+
+def _check_msm(pb, pts, scalars_list):
+    key = pb.CommitKey(bases_to_abi(pts))
+    got = key.commit_batch([to_abi(s) for s in scalars_list])
+    for g, s in zip(got, scalars_list):
+        want = R.jac_to_affine(R.msm_pippenger(pts, R.poly_trim(s)))
+        assert R.g1_from_raw_bytes(g.raw) == want
+        assert g.to_bytes() == R.g1_compress(want)
+
+
+@pytest.mark.parametrize("n", [1, 2, 23, 100, 700])
+def test_msm_matches_oracle(pb, n):
+    rng = random.Random(n)
+    pts = progression_bases(n, rng.randrange(1, R.R_MOD), rng.randrange(1, R.R_MOD))
+    _check_msm(pb, pts, [rand_fr(rng, n), rand_fr(rng, max(1, n // 2)), [rng.randrange(1 << 16) for _ in range(n)]])
+
+
+def test_msm_edge_cases(pb):
+    rng = random.Random(5)
+    n = 64
+    pts = progression_bases(n, 3, 5)
+    pts[7] = None  # identity base
+    pts[9] = pts[8]  # repeated point -> doubling inside a bucket
+    pts[11] = R.g1_neg(pts[10])  # P and -P in the same bucket -> cancellation
+    cases = [
+        [0] * n,
+        [1] * n,
+        [R.R_MOD - 1] * n,
+        [5] * n,  # all-equal scalars: one bucket per window
+        [rng.randrange(2) for _ in range(n)],
+        rand_fr(rng, n)[:-1] + [0],
+        [0] * (n - 1) + [7],
+    ]
+    _check_msm(pb, pts, cases)
+    key = pb.CommitKey(bases_to_abi(pts[:8]))
+    with pytest.raises(pb.PolynomialDegreeTooLarge):  # key.rs:816-824
+        key.commit(to_abi([1] * 9))
+    assert key.commit(to_abi([3] * 8 + [0])).raw  # trailing zeros are trimmed first
+
+
+def test_msm_large_known_discrete_log(pb):
+    """2^16 points: bases [p0 + i*b] G so the answer is a single scalar multiplication."""
+    rng = random.Random(16)
+    n = (1 << 16) + 7
+    p0, step = rng.randrange(1, R.R_MOD), rng.randrange(1, R.R_MOD)
+    pts = progression_bases(n, p0, step)
+    key = pb.CommitKey(bases_to_abi(pts))
+    polys = [rand_fr(rng, n - 5), rand_fr(rng, n), rand_fr(rng, n - 6), rand_fr(rng, 1 << 15)]
+    got = key.commit_batch([to_abi(p) for p in polys])
+    for g, s in zip(got, polys):
+        k = sum(si * (p0 + i * step) for i, si in enumerate(s)) % R.R_MOD
+        assert R.g1_from_raw_bytes(g.raw) == R.g1_mul(R.G1_GEN, k)
