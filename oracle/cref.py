@@ -1,0 +1,109 @@
+"""ctypes wrapper around oracle/_build/libcref.so (the multi-threaded C++ restatement).
+
+TEST INFRASTRUCTURE / CPU BASELINE ONLY - never imported from plonk_b200/."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import List, Optional, Sequence
+
+from . import pyref as R
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libcref.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            subprocess.check_call(["make", "-C", _HERE])
+        L = ctypes.CDLL(_SO)
+        c = ctypes
+        L.cref_ntt.argtypes = [c.c_void_p, c.c_size_t, c.c_void_p, c.c_uint32, c.c_int, c.c_int, c.c_int]
+        L.cref_msm.argtypes = [c.c_void_p, c.c_void_p, c.c_size_t, c.c_void_p, c.c_int]
+        L.cref_srs_from_secret.argtypes = [c.c_size_t, c.c_void_p, c.c_void_p, c.c_void_p, c.c_int]
+        L.cref_prover_new.restype = c.c_void_p
+        L.cref_prover_new.argtypes = [c.c_void_p, c.c_size_t, c.c_size_t, c.c_void_p, c.c_void_p, c.c_size_t, c.c_void_p, c.c_size_t, c.c_int]
+        L.cref_prover_free.argtypes = [c.c_void_p]
+        L.cref_prover_commitments.argtypes = [c.c_void_p, c.c_void_p]
+        L.cref_prove.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_size_t, c.c_void_p, c.c_void_p]
+        _lib = L
+    return _lib
+
+
+def threads() -> int:
+    return lib().cref_threads()
+
+
+def ntt(data: bytes, log_n: int, inverse: int, coset: int, nthreads: Optional[int] = None) -> bytes:
+    out = ctypes.create_string_buffer(32 << log_n)
+    lib().cref_ntt(data, len(data) // 32, out, log_n, inverse, coset, nthreads or threads())
+    return out.raw
+
+
+def msm(bases_raw: bytes, scalars: bytes, nthreads: Optional[int] = None) -> bytes:
+    n = min(len(bases_raw) // 96, len(scalars) // 32)
+    out = ctypes.create_string_buffer(96)
+    lib().cref_msm(bases_raw, scalars, n, out, nthreads or threads())
+    return out.raw
+
+
+def srs_from_secret(n: int, x: int, g_scalar: int, nthreads: Optional[int] = None) -> bytes:
+    out = ctypes.create_string_buffer(96 * n)
+    lib().cref_srs_from_secret(n, R.fr_to_mont_bytes(x), R.fr_to_mont_bytes(g_scalar), out, nthreads or threads())
+    return out.raw
+
+
+class CircuitArrays:
+    """Flat description of a composed circuit, shared by the C++ oracle and the GPU prover:
+    11 selector columns (Montgomery Fr), 4 wire columns (u32 witness indices), witnesses,
+    sorted public-input positions and values."""
+
+    def __init__(self, comp: R.Composer):
+        n = len(comp.constraints)
+        self.constraints = n
+        self.selectors = b"".join(R.fr_vec_to_mont_bytes([g.sel[k] for g in comp.constraints]) for k in R.SELECTORS)
+        cols = [[g.a for g in comp.constraints], [g.b for g in comp.constraints], [g.c for g in comp.constraints], [g.d for g in comp.constraints]]
+        self.wires = b"".join(int(w).to_bytes(4, "little") for col in cols for w in col)
+        self.n_witnesses = len(comp.witnesses)
+        self.witnesses = R.fr_vec_to_mont_bytes(comp.witnesses)
+        idx = comp.public_input_indexes()
+        self.pi_idx = b"".join(i.to_bytes(8, "little") for i in idx)
+        self.pi_vals = R.fr_vec_to_mont_bytes(comp.public_inputs_vec())
+        self.n_pi = len(idx)
+
+
+def draw_blinders(rng: R.StdRng) -> bytes:
+    """The 14 BlsScalar::random draws of one Prover::prove call, in RNG order (prover.rs:154-161,
+    503, 553-555)."""
+    return R.fr_vec_to_mont_bytes([R.fr_random(rng) for _ in range(14)])
+
+
+class CrefProver:
+    def __init__(self, label: bytes, arrays: CircuitArrays, srs_raw: bytes, nthreads: Optional[int] = None):
+        self.arrays = arrays
+        self._h = lib().cref_prover_new(label, len(label), arrays.constraints, arrays.selectors, arrays.wires,
+                                        arrays.n_witnesses, srs_raw, len(srs_raw) // 96, nthreads or threads())
+        if not self._h:
+            raise ValueError("cref_prover_new failed (SRS too small?)")
+
+    def commitments(self) -> List[bytes]:
+        out = ctypes.create_string_buffer(48 * 15)
+        lib().cref_prover_commitments(self._h, out)
+        return [out.raw[48 * i : 48 * (i + 1)] for i in range(15)]
+
+    def prove(self, blinders: bytes, arrays: Optional[CircuitArrays] = None) -> bytes:
+        a = arrays or self.arrays
+        out = ctypes.create_string_buffer(1008)
+        rc = lib().cref_prove(self._h, a.witnesses, a.pi_idx, a.pi_vals, a.n_pi, blinders, out)
+        if rc != 0:
+            raise ValueError(f"cref_prove failed: {rc}")
+        return out.raw
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().cref_prover_free(self._h)
+            self._h = None

@@ -215,12 +215,20 @@ Fr ntt_group_gen(int log_n, bool inverse) {  // group_gen / group_gen_inv
   for (int i = log_n; i < 32; i++) g = g.sqr();
   return inverse ? g.inv() : g;
 }
-Fr ntt_size_inv(int log_n) {
+static Fr ntt_size_inv_compute(int log_n) {
   uint32_t l[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   l[log_n / 32] = 1u << (log_n % 32);
   Fr x;
   for (int i = 0; i < 8; i++) x.v[i] = l[i];
   return x.to_mont().inv();
+}
+Fr ntt_size_inv(int log_n) {  // cached: the host-side inversion costs ~0.1 ms
+  static Fr cache[32];
+  static std::once_flag once;
+  std::call_once(once, [] {
+    for (int i = 0; i < 32; i++) cache[i] = ntt_size_inv_compute(i);
+  });
+  return cache[log_n];
 }
 Fr ntt_coset_gen(bool inverse) {
   Fr g = fr_from_canonical(kGenerator);
@@ -335,6 +343,13 @@ int ntt_run(const uint64_t* d_in, size_t in_len, uint64_t* d_out, uint32_t log_n
   if (coset && !inverse && in_len > 0) PB_TRY(get_coset_fwd(n, st, &pre));
   if (coset && inverse) PB_TRY(get_coset_inv((int)log_n, st, &post));
 
+  // The last pass scatters to digit-reversed positions, so it cannot run in place: with more
+  // than one pass the intermediate passes work in a stream-ordered scratch buffer and the last
+  // pass writes the caller's buffer.  (A single pass is one CTA per vector: loads finish before
+  // stores begin, so in == out is fine there.)
+  uint64_t* d_tmp = nullptr;
+  if (n_pass > 1) PB_CUDA(cudaMallocAsync((void**)&d_tmp, (size_t)batch * n * 32, st));
+
   int log_h = 0;
   for (int q = 0; q < n_pass; q++) {
     PassArgs a;
@@ -348,11 +363,11 @@ int ntt_run(const uint64_t* d_in, size_t in_len, uint64_t* d_out, uint32_t log_n
     a.log_r0 = (n_pass > 1) ? radices[0] : 0;
     const int room = kMaxLogTile - a.r;
     a.log_t = a.last ? (a.log_r0 < room ? a.log_r0 : room) : (log_lo < room ? log_lo : room);
-    a.in = (const uint4*)(a.first ? d_in : d_out);
-    a.out = (uint4*)d_out;
+    a.in = (const uint4*)(a.first ? d_in : d_tmp);
+    a.out = (uint4*)(a.last ? d_out : d_tmp);
     a.in_len = a.first ? in_len : n;
-    a.in_stride = a.first ? in_stride : out_stride;
-    a.out_stride = out_stride;
+    a.in_stride = a.first ? in_stride : n;
+    a.out_stride = a.last ? out_stride : n;
     PB_TRY(get_twiddles(a.r, inverse != 0, st, &a.w_r));
     a.w_m = nullptr;
     if (!a.last) PB_TRY(get_twiddles(a.r + log_lo, inverse != 0, st, &a.w_m));
@@ -366,6 +381,7 @@ int ntt_run(const uint64_t* d_in, size_t in_len, uint64_t* d_out, uint32_t log_n
     PB_CUDA(cudaGetLastError());
     log_h += a.r;
   }
+  if (d_tmp) PB_CUDA(cudaFreeAsync(d_tmp, st));
   return 0;
 }
 
