@@ -93,6 +93,36 @@ int pb200_g1_compress(const uint64_t* affine_raw, uint8_t out48[48]);
 /* out = a + b for two points in the 96-byte raw layout (host-side helper for multi-GPU reduction). */
 int pb200_g1_add_affine(const uint64_t* a_raw, const uint64_t* b_raw, uint64_t* out_raw);
 
+/* ---- device-resident prover (Prover::new / Prover::prove, PlonkVersion::V3) ------------------ */
+/* Circuit description = what Compiler::preprocess reads from the Composer (src/compiler.rs:132-170):
+ *   selectors: 11 columns x n_constraints Fr in the order q_m, q_l, q_r, q_o, q_f, q_c, q_arith,
+ *              q_range, q_logic, q_fixed_group_add, q_variable_group_add (column-major);
+ *   wires:     4 columns (a, b, c, d) x n_constraints witness indices;
+ *   srs_raw:   PublicParameters' commit key, 96-byte raw points; it is trimmed here exactly as
+ *              pp.trim(next_pow2(constraints + 6)) does (compiler.rs:121-124, srs.rs:188-196).
+ * Preprocessing (15 iNTT, 15 commitments, 16 coset NTTs, sigma evaluations) runs on the GPU and
+ * the prover key stays resident in HBM. */
+int pb200_prover_new(const uint8_t* label, size_t label_len, size_t n_constraints,
+                     const uint64_t* selectors, const uint32_t* wires, size_t n_witnesses,
+                     const uint8_t* srs_raw, size_t n_srs_points, pb200_prover_t** out);
+void pb200_prover_free(pb200_prover_t* prover);
+/* 15 compressed commitments (verifier-key material) in the order of `selectors` then s_sigma_1..4. */
+int pb200_prover_commitments(const pb200_prover_t* prover, uint8_t* out_15x48);
+/* One proof.  witnesses: the Composer's witness table after running the circuit (n_witnesses Fr);
+ * pi_idx / pi_vals: sorted public-input positions and values (Composer::public_input_indexes /
+ * public_inputs, src/composer.rs:465-480); blinders: the 14 BlsScalar::random draws of
+ * prove_inner in RNG order a0,a1,b0,b1,c0,c1,d0,d1, z0,z1,z2, b12,b13,b14 (prover.rs:154-161,
+ * 503, 553-555) - the RNG belongs to the caller, as in the reference API.
+ * out_proof: Proof::to_bytes, 1008 bytes (src/proof_system/proof.rs:137-162).
+ * Returns PB200_ERR_UNSATISFIED for Error::CircuitUnsatisfied. */
+int pb200_prove(const pb200_prover_t* prover, const uint64_t* witnesses, size_t n_witnesses,
+                const uint64_t* pi_idx, const uint64_t* pi_vals, size_t n_pi,
+                const uint64_t* blinders, uint8_t* out_proof);
+/* Same with the witness table already resident in HBM (pi_* and blinders stay host pointers). */
+int pb200_prove_dev(const pb200_prover_t* prover, const uint64_t* d_witnesses,
+                    const uint64_t* pi_idx, const uint64_t* pi_vals, size_t n_pi,
+                    const uint64_t* blinders, uint8_t* out_proof, void* stream);
+
 /* ---- measurement helpers ----------------------------------------------------------------- */
 /* Register-only IMAD.WIDE microbenchmark: returns achieved 32x32+64 multiply-adds per second. */
 int pb200_imad_peak(double* mads_per_sec);

@@ -9,3 +9,4 @@ Everything computes on the GPU through the C ABI in include/plonk_b200.h; there 
 from ._lib import Pb200Error, lib  # noqa: F401
 from .domain import EvaluationDomain  # noqa: F401
 from .kzg import CommitKey, Commitment, PolynomialDegreeTooLarge  # noqa: F401
+from .prover import CircuitUnsatisfied, Prover  # noqa: F401

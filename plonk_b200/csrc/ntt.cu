@@ -244,6 +244,20 @@ struct TableCache {
 };
 static TableCache g_tables;
 
+// out[i] = scale * base^i for i < n, into an existing device buffer.
+int fill_powers(uint4* out, size_t n, const Fr& base, const Fr& scale, cudaStream_t st) {
+  PowArgs pa;
+  Fr p = base;
+  for (int b = 0; b < 32; b++) {
+    pa.p2[b] = p;
+    p = p.sqr();
+  }
+  pa.scale = scale;
+  PB_LAUNCH(k_powers, div_up(n, 256), 256, 0, st, out, n, pa);
+  PB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 static int build_powers(uint4** out, size_t n, const Fr& base, const Fr& scale, cudaStream_t st) {
   PB_CUDA(cudaMalloc((void**)out, n * 32));
   PowArgs pa;
@@ -260,7 +274,7 @@ static int build_powers(uint4** out, size_t n, const Fr& base, const Fr& scale, 
 
 // All table builds are issued on the caller's stream under the cache mutex; a consumer on another
 // stream must not race with the build, so we synchronise the building stream once per new table.
-static int get_twiddles(int logm, bool inverse, cudaStream_t st, const uint4** out) {
+int get_twiddles(int logm, bool inverse, cudaStream_t st, const uint4** out) {
   std::lock_guard<std::mutex> lk(g_tables.mu);
   uint4*& slot = g_tables.w[inverse ? 1 : 0][logm];
   if (!slot) {

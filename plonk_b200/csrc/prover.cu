@@ -1,0 +1,962 @@
+// Device-resident PLONK prover: Prover::new / Prover::prove (PlonkVersion::V3) of the reference
+// (src/compiler/prover.rs:53-115, 415-761; preprocessing as Compiler::preprocess,
+// src/compiler.rs:132-461) with every polynomial kept in HBM between rounds.
+//
+// The two hot kernels (NTT: ntt.cu, G1 MSM: msm.cu) are driven exactly where the reference calls
+// domain.{ifft,coset_fft,coset_ifft} and commit_key.commit; the O(n) glue between them
+//  runs as small streaming kernels here so that per proof only the
+// witnesses go up and 11 x 96 B commitments + 15 x 32 B evaluations come down:
+//   round 1  gather wires -> 4 x iNTT(n) -> blind -> 4 commitments            prover.rs:446-479
+//   round 2  grand product (batched inversion + prefix-product scan) -> iNTT -> commit  :483-505,
+//            composer/permutation.rs:213-294
+//   round 3  6 x coset NTT(8n) -> fused gate/permutation quotient kernel -> coset iNTT(8n)
+//            -> split + blind -> 4 commitments            quotient_poly.rs:20-310, prover.rs:545-589
+//   round 4  15 evaluations (chunked Horner + tree sum)                          prover.rs:593-658
+//   round 5  linearisation + both aggregate witnesses as one linear combination per opening,
+//            division by (X - z) as a suffix scan, 2 commitments   linearization_poly.rs:168-231,
+//            key.rs:394-417, polynomial.rs:345-367
+// The Fiat-Shamir transcript (transcript.h) and a handful of scalar formulas run on the host
+// between rounds.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "host_field.h"
+#include "transcript.h"
+
+struct pb200_srs;
+
+namespace pb {
+
+int ntt_run(const uint64_t* d_in, size_t in_len, uint64_t* d_out, uint32_t log_n, int inverse, int coset,
+            uint32_t batch, size_t in_stride, size_t out_stride, cudaStream_t st);
+int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_t n, uint32_t batch,
+            size_t stride, uint64_t* out_affine_host, cudaStream_t st);
+int srs_upload(const uint8_t* raw, size_t n_points, pb200_srs** out);
+void srs_free(pb200_srs* s);
+size_t srs_len(const pb200_srs* s);
+int get_twiddles(int logm, bool inverse, cudaStream_t st, const uint4** out);
+int fill_powers(uint4* out, size_t n, const Fr& base, const Fr& scale, cudaStream_t st);
+Fr ntt_group_gen(int log_n, bool inverse);
+Fr ntt_size_inv(int log_n);
+Fr ntt_coset_gen(bool inverse);
+
+enum { Q_M, Q_L, Q_R, Q_O, Q_F, Q_C, Q_ARITH, Q_RANGE, Q_LOGIC, Q_FIXED, Q_VAR, S1, S2, S3, S4, N_POLY };
+
+PB_D Fr ldg_fr(const uint4* p, size_t i) {
+  uint4 a = __ldg(p + 2 * i), b = __ldg(p + 2 * i + 1);
+  Fr r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+PB_D Fr ld_fr_plain(const uint4* p, size_t i) {
+  uint4 a = p[2 * i], b = p[2 * i + 1];
+  Fr r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+PB_D void stg_fr(uint4* p, size_t i, const Fr& r) {
+  p[2 * i] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  p[2 * i + 1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+PB_D Fr lds_pair(const uint4* s) {  // two consecutive uint4 in shared memory
+  uint4 a = s[0], b = s[1];
+  Fr r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+PB_D Fr fr_small(uint32_t x) {  // Montgomery form of a small constant
+  Fr r = Fr::zero();
+  r.v[0] = x;
+  return r.to_mont();
+}
+
+// ---------------------------------------------------------------------------------------------
+// small streaming kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void k_gather_wires(const uint4* wit, const uint32_t* wires, size_t constraints, size_t n, uint4* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned k = blockIdx.y;
+  Fr v = Fr::zero();
+  if (i < constraints) v = ldg_fr(wit, wires[k * constraints + i]);
+  stg_fr(out, (size_t)k * n + i, v);
+}
+
+// coeffs[i] -= b_i ; coeffs[n + i] = b_i  (Prover::blind_poly_with_blinders, prover.rs:139-152)
+struct BlindArgs {
+  Fr b[4][3];
+  int nb;
+  int npoly;
+};
+__global__ void k_blind(uint4* polys, size_t stride, size_t n, BlindArgs a) {
+  const int t = threadIdx.x;
+  if (t >= a.npoly * a.nb) return;
+  const int p = t / a.nb, i = t % a.nb;
+  uint4* c = polys + 2 * (size_t)p * stride;
+  stg_fr(c, i, ld_fr_plain(c, i) - a.b[p][i]);
+  stg_fr(c, n + i, a.b[p][i]);
+}
+
+__global__ void k_zero(uint4* p, size_t n_elems) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_elems) stg_fr(p, i, Fr::zero());
+}
+
+// sigma Lagrange values: K_col * w^idx for the encoded permutation target (col << 40 | idx)
+__global__ void k_sigma_lagrange(const unsigned long long* sig, size_t n, const uint4* w_half, uint4* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 4 * n) return;
+  const unsigned long long e = sig[i];
+  const unsigned col = (unsigned)(e >> 40);
+  const size_t idx = (size_t)(e & 0xffffffffffull);
+  Fr root = (idx < n / 2 || n == 1) ? ldg_fr(w_half, idx) : ldg_fr(w_half, idx - n / 2).neg();
+  const uint32_t ks[4] = {1, 7, 13, 17};
+  stg_fr(out, i, root * fr_small(ks[col]));
+}
+
+// numerators and denominators of the grand product (permutation.rs:252-294)
+__global__ void k_perm_terms(const uint4* wv, const uint4* sigma, const uint4* w_half, size_t n, Fr beta, Fr gamma,
+                             uint4* num, uint4* den) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr root = (i < n / 2 || n == 1) ? ldg_fr(w_half, i) : ldg_fr(w_half, i - n / 2).neg();
+  Fr br = beta * root;
+  Fr a = ldg_fr(wv, i), b = ldg_fr(wv, n + i), c = ldg_fr(wv, 2 * n + i), d = ldg_fr(wv, 3 * n + i);
+  Fr nu = (a + br + gamma) * (b + br * fr_small(7) + gamma) * (c + br * fr_small(13) + gamma) * (d + br * fr_small(17) + gamma);
+  Fr de = (a + beta * ldg_fr(sigma, i) + gamma) * (b + beta * ldg_fr(sigma, n + i) + gamma) *
+          (c + beta * ldg_fr(sigma, 2 * n + i) + gamma) * (d + beta * ldg_fr(sigma, 3 * n + i) + gamma);
+  stg_fr(num, i, nu);
+  stg_fr(den, i, de);
+}
+
+// out[i] = a[i] / b[i] (a may be null: out = 1/b).  Montgomery's trick over chunks of 8 per thread;
+// zeros are left as zeros like util::batch_inversion (util.rs:87-118).
+__global__ void k_batch_div(const uint4* a, const uint4* b, size_t n, uint4* out) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t base = t * 8;
+  if (base >= n) return;
+  Fr x[8], p[8];
+  Fr acc = Fr::one();
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    x[k] = (base + k < n) ? ld_fr_plain(b, base + k) : Fr::one();
+    if (!x[k].is_zero()) acc = acc * x[k];
+    p[k] = acc;
+  }
+  Fr inv = acc.inv();
+#pragma unroll
+  for (int k = 7; k >= 0; k--) {
+    if (base + k >= n) continue;
+    Fr r;
+    if (x[k].is_zero()) {
+      r = Fr::zero();
+    } else {
+      r = (k > 0) ? inv * p[k - 1] : inv;
+      inv = inv * x[k];
+    }
+    if (a) r = r * ld_fr_plain(a, base + k);
+    stg_fr(out, base + k, r);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Scan over Fr (op = multiply or add), exclusive, optional reversed index order.
+// Phase 1: 256 threads x 8 elements per CTA; phase 2: scan of the CTA totals; phase 3: fix-up.
+// ---------------------------------------------------------------------------------------------
+template <bool MUL>
+PB_D Fr scan_op(const Fr& a, const Fr& b) {
+  return MUL ? a * b : a + b;
+}
+template <bool MUL>
+PB_D Fr scan_id() {
+  return MUL ? Fr::one() : Fr::zero();
+}
+
+template <bool MUL, bool REV>
+__global__ void __launch_bounds__(256) k_scan_local(const uint4* in, size_t n, uint4* out, uint4* totals) {
+  __shared__ uint4 sh[2][256][2];
+  const int tid = threadIdx.x;
+  const size_t base = ((size_t)blockIdx.x * 256 + tid) * 8;
+  Fr p[8];
+  Fr acc = scan_id<MUL>();
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const size_t i = base + k;
+    Fr x = (i < n) ? ld_fr_plain(in, REV ? (n - 1 - i) : i) : scan_id<MUL>();
+    acc = scan_op<MUL>(acc, x);
+    p[k] = acc;
+  }
+  int cur = 0;
+  sh[0][tid][0] = make_uint4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
+  sh[0][tid][1] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
+  __syncthreads();
+  for (int d = 1; d < 256; d <<= 1) {
+    Fr v = lds_pair(sh[cur][tid]);
+    if (tid >= d) v = scan_op<MUL>(lds_pair(sh[cur][tid - d]), v);
+    sh[cur ^ 1][tid][0] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
+    sh[cur ^ 1][tid][1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+    cur ^= 1;
+    __syncthreads();
+  }
+  Fr prefix = (tid > 0) ? lds_pair(sh[cur][tid - 1]) : scan_id<MUL>();
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const size_t i = base + k;
+    if (i < n) {
+      Fr v = (k > 0) ? scan_op<MUL>(prefix, p[k - 1]) : prefix;
+      stg_fr(out, REV ? (n - 1 - i) : i, v);
+    }
+  }
+  if (tid == 255 && totals) {
+    Fr tot = lds_pair(sh[cur][255]);
+    stg_fr(totals, blockIdx.x, tot);
+  }
+}
+
+template <bool MUL, bool REV>
+__global__ void k_scan_fixup(uint4* out, size_t n, const uint4* block_prefix) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t blk = i / 2048;
+  if (blk == 0) return;
+  const size_t j = REV ? (n - 1 - i) : i;
+  stg_fr(out, j, scan_op<MUL>(ld_fr_plain(block_prefix, blk), ld_fr_plain(out, j)));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Quotient numerator on the 8n coset (quotient_poly.rs:160-310 + all widget compute_quotient_i)
+// ---------------------------------------------------------------------------------------------
+struct QuotArgs {
+  const uint4* w8;      // [6][8n]: z, a, b, c, d, pi coset evaluations
+  const uint4* key8;    // [15][8n] prover-key coset evaluations (enum order)
+  const uint4* linear8; // [8n]
+  const uint4* l1_8;    // [8n] L_1 on the coset (without alpha^2)
+  uint4* out;           // [8n]
+  size_t n8;
+  Fr alpha, beta, gamma, alpha_sq, ch_range, ch_logic, ch_fixed, ch_var;
+  Fr vh_inv[8];
+  int has_range, has_logic, has_fixed, has_var;
+};
+
+PB_D Fr delta4(const Fr& f) {
+  const Fr one = Fr::one();
+  Fr f1 = f - one, f2 = f1 - one, f3 = f2 - one;
+  return f * f1 * f2 * f3;
+}
+PB_D Fr mul_small(const Fr& x, int k) {  // k * x for small positive k by additions
+  Fr acc = Fr::zero(), p = x;
+  while (k) {
+    if (k & 1) acc = acc + p;
+    p = p.dbl();
+    k >>= 1;
+  }
+  return acc;
+}
+PB_D Fr edwards_d() {  // dusk_jubjub::EDWARDS_D = -(10240/10241) mod r, canonical limbs
+  Fr d;
+  d.v[0] = 0xd6343eb1u; d.v[1] = 0x01065fd6u; d.v[2] = 0x37579d26u; d.v[3] = 0x292d7f6du;
+  d.v[4] = 0xe6bd7fd4u; d.v[5] = 0xf5fd9207u; d.v[6] = 0x4bfa2b48u; d.v[7] = 0x2a9318e7u;
+  return d.to_mont();
+}
+
+struct WireVals {
+  Fr a, b, c, d, a_w, b_w, d_w;
+};
+PB_D Fr widget_range(const Fr& ch, const WireVals& v) {  // range/proverkey.rs:32-57 (without selector)
+  Fr k = ch.sqr(), k2 = k.sqr(), k3 = k2 * k;
+  Fr t = delta4(v.c - mul_small(v.d, 4)) + delta4(v.b - mul_small(v.c, 4)) * k + delta4(v.a - mul_small(v.b, 4)) * k2 +
+         delta4(v.d_w - mul_small(v.a, 4)) * k3;
+  return t * ch;
+}
+PB_D Fr widget_logic(const Fr& ch, const Fr& q_c, const WireVals& v) {  // logic/proverkey.rs:34-71, 120-144
+  Fr k = ch.sqr(), k2 = k.sqr(), k3 = k2 * k, k4 = k3 * k;
+  Fr A = v.a_w - mul_small(v.a, 4), B = v.b_w - mul_small(v.b, 4), D = v.d_w - mul_small(v.d, 4);
+  const Fr& w = v.c;
+  Fr ab = A + B;
+  Fr F = w * (w * (mul_small(w, 4) - mul_small(ab, 18) + fr_small(81)) + mul_small(A.sqr() + B.sqr(), 18) - mul_small(ab, 81) + fr_small(83));
+  Fr E = mul_small(ab + D, 3) - F.dbl();
+  Fr Bq = q_c * (mul_small(D, 9) - mul_small(ab, 3));
+  Fr t = delta4(A) + delta4(B) * k + delta4(D) * k2 + (w - A * B) * k3 + (Bq + E) * k4;
+  return t * ch;
+}
+PB_D Fr widget_fixed(const Fr& ch, const Fr& q_l, const Fr& q_r, const Fr& q_c, const WireVals& v) {  // fixed_base/proverkey.rs:39-103
+  const Fr one = Fr::one();
+  Fr k = ch.sqr(), k2 = k.sqr(), k3 = k2 * k;
+  Fr bit = v.d_w - v.d - v.d;
+  Fr bit_c = bit * (bit - one) * (bit + one);
+  Fr y_alpha = bit.sqr() * (q_r - one) + one, x_alpha = bit * q_l;
+  Fr xy = (bit * q_c - v.c) * k;
+  Fr t = v.c * v.a * v.b * edwards_d();
+  Fr xa = ((v.a_w + v.a_w * t) - (v.a * y_alpha + v.b * x_alpha)) * k2;
+  Fr ya = ((v.b_w - v.b_w * t) - (v.b * y_alpha + v.a * x_alpha)) * k3;
+  return (bit_c + xa + ya + xy) * ch;
+}
+PB_D Fr widget_var(const Fr& ch, const WireVals& v) {  // curve_addition/proverkey.rs:33-79
+  Fr k = ch.sqr();
+  const Fr &x1 = v.a, &x3 = v.a_w, &y1 = v.b, &y3 = v.b_w, &x2 = v.c, &y2 = v.d, &x1y2 = v.d_w;
+  Fr xy = x1 * y2 - x1y2, y1x2 = y1 * x2, y1y2 = y1 * y2, x1x2 = x1 * x2;
+  Fr t = edwards_d() * x1y2 * y1x2;
+  Fr x3c = ((x1y2 + y1x2) - (x3 + x3 * t)) * k;
+  Fr y3c = ((y1y2 + x1x2) - (y3 - y3 * t)) * k.sqr();
+  return (xy + x3c + y3c) * ch;
+}
+
+__global__ void __launch_bounds__(128) k_quotient(QuotArgs q) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= q.n8) return;
+  const size_t n8 = q.n8, iw = (i + 8) & (n8 - 1);
+  WireVals v;
+  const Fr z = ldg_fr(q.w8, i), z_w = ldg_fr(q.w8, iw);
+  v.a = ldg_fr(q.w8, n8 + i); v.a_w = ldg_fr(q.w8, n8 + iw);
+  v.b = ldg_fr(q.w8, 2 * n8 + i); v.b_w = ldg_fr(q.w8, 2 * n8 + iw);
+  v.c = ldg_fr(q.w8, 3 * n8 + i);
+  v.d = ldg_fr(q.w8, 4 * n8 + i); v.d_w = ldg_fr(q.w8, 4 * n8 + iw);
+  const Fr pi = ldg_fr(q.w8, 5 * n8 + i);
+#define KEY(k) ldg_fr(q.key8, (size_t)(k) * n8 + i)
+  const Fr q_l = KEY(Q_L), q_r = KEY(Q_R), q_c = KEY(Q_C);
+  // arithmetic/proverkey.rs:44-69
+  Fr t = (v.a * v.b * KEY(Q_M) + v.a * q_l + v.b * q_r + v.c * KEY(Q_O) + v.d * KEY(Q_F) + q_c) * KEY(Q_ARITH);
+  if (q.has_range) t = t + widget_range(q.ch_range, v) * KEY(Q_RANGE);
+  if (q.has_logic) t = t + widget_logic(q.ch_logic, q_c, v) * KEY(Q_LOGIC);
+  if (q.has_fixed) t = t + widget_fixed(q.ch_fixed, q_l, q_r, q_c, v) * KEY(Q_FIXED);
+  if (q.has_var) t = t + widget_var(q.ch_var, v) * KEY(Q_VAR);
+  t = t + pi;
+  // permutation/proverkey.rs:40-125
+  const Fr x = ldg_fr(q.linear8, i);
+  const Fr bx = q.beta * x;
+  Fr ident = (v.a + bx + q.gamma) * (v.b + mul_small(bx, 7) + q.gamma) * (v.c + mul_small(bx, 13) + q.gamma) *
+             (v.d + mul_small(bx, 17) + q.gamma) * z * q.alpha;
+  Fr copy = (v.a + q.beta * KEY(S1) + q.gamma) * (v.b + q.beta * KEY(S2) + q.gamma) * (v.c + q.beta * KEY(S3) + q.gamma) *
+            (v.d + q.beta * KEY(S4) + q.gamma) * z_w * q.alpha;
+#undef KEY
+  Fr l1 = ldg_fr(q.l1_8, i) * q.alpha_sq;
+  t = t + ident - copy + (z - Fr::one()) * l1;
+  stg_fr(q.out, i, t * q.vh_inv[i & 7]);
+}
+
+// flag |= any nonzero element in p[lo, hi)
+__global__ void k_any_nonzero(const uint4* p, size_t lo, size_t hi, unsigned* flag) {
+  size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hi) return;
+  uint4 a = p[2 * i], b = p[2 * i + 1];
+  if (a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) atomicOr(flag, 1u);
+}
+
+// split t(X) into four polynomials of stride `stride` and apply b12..b14 (prover.rs:545-574)
+__global__ void k_split_quotient(const uint4* t, size_t n, size_t n8, size_t stride, Fr b12, Fr b13, Fr b14, uint4* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= stride) return;
+  const unsigned k = blockIdx.y;
+  Fr v = Fr::zero();
+  if (k < 3) {
+    if (i < n) v = ld_fr_plain(t, (size_t)k * n + i);
+    if (i == n) v = (k == 0) ? b12 : (k == 1 ? b13 : b14);
+    if (i == 0 && k == 1) v = v - b12;
+    if (i == 0 && k == 2) v = v - b13;
+  } else {
+    if (3 * n + i < n8) v = ld_fr_plain(t, 3 * n + i);
+    if (i == 0) v = v - b14;
+  }
+  stg_fr(out, (size_t)k * stride + i, v);
+}
+
+// Polynomial::evaluate for a batch of (poly, point) jobs: chunked Horner + CTA tree sum.
+struct EvalJobs {
+  const uint4* poly[16];
+  unsigned len[16];
+  Fr point[16];
+  int njobs;
+};
+__global__ void __launch_bounds__(256) k_poly_eval(EvalJobs jobs, uint4* partial, unsigned nblocks) {
+  __shared__ uint4 sh[256][2];
+  const int j = blockIdx.y, tid = threadIdx.x;
+  const size_t base = ((size_t)blockIdx.x * 256 + tid) * 8;
+  const unsigned len = jobs.len[j];
+  Fr acc = Fr::zero();
+  if (base < len) {
+    const Fr x = jobs.point[j];
+#pragma unroll
+    for (int k = 7; k >= 0; k--) {
+      Fr c = (base + k < len) ? ld_fr_plain(jobs.poly[j], base + k) : Fr::zero();
+      acc = acc * x + c;
+    }
+    acc = acc * x.pow_u64(base);
+  }
+  sh[tid][0] = make_uint4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
+  sh[tid][1] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
+  __syncthreads();
+  for (int d = 128; d > 0; d >>= 1) {
+    if (tid < d) {
+      Fr v = lds_pair(sh[tid]) + lds_pair(sh[tid + d]);
+      sh[tid][0] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
+      sh[tid][1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) stg_fr(partial, (size_t)j * nblocks + blockIdx.x, lds_pair(sh[0]));
+}
+__global__ void k_sum_rows(const uint4* partial, unsigned nblocks, uint4* out) {
+  const int j = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  Fr acc = Fr::zero();
+  for (unsigned b = 0; b < nblocks; b++) acc = acc + ld_fr_plain(partial, (size_t)j * nblocks + b);
+  stg_fr(out, j, acc);
+}
+
+// out[i] = sum_k coef[k] * poly[k][i]
+struct LinArgs {
+  const uint4* poly[24];
+  unsigned len[24];
+  Fr coef[24];
+  int nterms;
+};
+__global__ void k_lincomb(LinArgs a, size_t n, uint4* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr acc = Fr::zero();
+  for (int k = 0; k < a.nterms; k++)
+    if (i < a.len[k]) acc = acc + ld_fr_plain(a.poly[k], i) * a.coef[k];
+  stg_fr(out, i, acc);
+}
+
+// d[i] = c[i] * pw[i]
+__global__ void k_mul_pointwise(const uint4* a, const uint4* b, size_t n, uint4* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) stg_fr(out, i, ld_fr_plain(a, i) * ld_fr_plain(b, i));
+}
+// out[i] -= 1 ;  out[i] *= c[i & 7]
+__global__ void k_sub_one(uint4* p, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) stg_fr(p, i, ld_fr_plain(p, i) - Fr::one());
+}
+struct Period8 {
+  Fr c[8];
+};
+__global__ void k_scale_period8(uint4* p, size_t n, Period8 c) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) stg_fr(p, i, ld_fr_plain(p, i) * c.c[i & 7]);
+}
+
+}  // namespace pb
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+using pbh::HFr;
+
+struct pb200_prover {
+  std::vector<uint8_t> label;
+  size_t constraints = 0, n = 0, n8 = 0;
+  int log_n = 0;
+  pb200_srs* srs = nullptr;
+  uint32_t* d_wires = nullptr;  // [4][constraints]
+  uint4* d_polys = nullptr;     // [15][n]
+  uint4* d_key8 = nullptr;      // [15][8n]
+  uint4* d_linear8 = nullptr;   // [8n]
+  uint4* d_l1_8 = nullptr;      // [8n]
+  uint4* d_sigma = nullptr;     // [4][n]
+  HFr vh_inv[8];
+  int has_widget[4] = {0, 0, 0, 0};
+  uint8_t comm[pb::N_POLY][48];
+  size_t n_witnesses = 0;
+};
+
+namespace pb {
+
+static Fr to_dev(const HFr& x) {
+  Fr r;
+  memcpy(r.v, x.v, 32);
+  return r;
+}
+static HFr to_host(const Fr& x) {
+  HFr r;
+  memcpy(r.v, x.v, 32);
+  return r;
+}
+static HFr hfr_pow(const HFr& x, uint64_t e) { return x.pow(&e, 1); }
+
+template <bool MUL, bool REV>
+static int fr_scan(const uint4* in, size_t n, uint4* out, cudaStream_t st) {
+  const unsigned nblk = div_up(n, 2048);
+  uint4 *tot = nullptr, *tot_scan = nullptr;
+  PB_CUDA(cudaMallocAsync((void**)&tot, (size_t)nblk * 32, st));
+  PB_CUDA(cudaMallocAsync((void**)&tot_scan, (size_t)nblk * 32, st));
+  PB_LAUNCH((k_scan_local<MUL, REV>), nblk, 256, 0, st, in, n, out, tot);
+  if (nblk > 1) {
+    if (nblk > 2048) return fail(PB200_ERR_INVALID_ARG, "scan too large");
+    PB_LAUNCH((k_scan_local<MUL, false>), 1, 256, 0, st, (const uint4*)tot, (size_t)nblk, tot_scan, (uint4*)nullptr);
+    PB_LAUNCH((k_scan_fixup<MUL, REV>), div_up(n, 256), 256, 0, st, out, n, (const uint4*)tot_scan);
+  }
+  PB_CUDA(cudaGetLastError());
+  cudaFreeAsync(tot, st);
+  cudaFreeAsync(tot_scan, st);
+  return 0;
+}
+
+static void compress_affine(const uint64_t* raw, uint8_t out[48]) { pbh::g1_compress_raw(raw, out); }
+
+int prover_new(const uint8_t* label, size_t label_len, size_t constraints, const uint64_t* selectors,
+               const uint32_t* wires, size_t n_witnesses, const uint8_t* srs_raw, size_t n_srs, pb200_prover** out) {
+  if (constraints == 0) return fail(PB200_ERR_INVALID_ARG, "empty circuit");
+  cudaStream_t st = thread_stream();
+  pb200_prover* P = new pb200_prover();
+  P->label.assign(label, label + label_len);
+  P->constraints = constraints;
+  P->n_witnesses = n_witnesses;
+  size_t n_trim = 1;
+  while (n_trim < constraints + 6) n_trim <<= 1;  // compiler.rs:121-124
+  size_t keep = n_trim + 6;                       // srs.rs:188-196
+  if (keep + 1 > n_srs) {
+    delete P;
+    return fail(PB200_ERR_DEGREE_TOO_LARGE, "public parameters too small for this circuit (TruncatedDegreeTooLarge)");
+  }
+  size_t n = 1;
+  int log_n = 0;
+  while (n < constraints) {
+    n <<= 1;
+    log_n++;
+  }
+  P->n = n;
+  P->n8 = 8 * n;
+  P->log_n = log_n;
+  if (log_n + 3 >= 32) {
+    delete P;
+    return fail(PB200_ERR_INVALID_DOMAIN, "quotient domain too large");
+  }
+  PB_TRY(srs_upload(srs_raw, keep + 1, &P->srs));
+  const size_t n8 = P->n8;
+  PB_CUDA(cudaMalloc((void**)&P->d_wires, 4 * constraints * 4));
+  PB_CUDA(cudaMalloc((void**)&P->d_polys, (size_t)N_POLY * n * 32));
+  PB_CUDA(cudaMalloc((void**)&P->d_key8, (size_t)N_POLY * n8 * 32));
+  PB_CUDA(cudaMalloc((void**)&P->d_linear8, n8 * 32));
+  PB_CUDA(cudaMalloc((void**)&P->d_l1_8, n8 * 32));
+  PB_CUDA(cudaMalloc((void**)&P->d_sigma, 4 * n * 32));
+  PB_CUDA(cudaMemcpyAsync(P->d_wires, wires, 4 * constraints * 4, cudaMemcpyHostToDevice, st));
+
+  // selector columns, zero padded to n, then iNTT -> coefficient form (compiler.rs:149-211)
+  uint4* cols = nullptr;
+  PB_CUDA(cudaMallocAsync((void**)&cols, (size_t)N_POLY * n * 32, st));
+  PB_CUDA(cudaMemsetAsync(cols, 0, (size_t)N_POLY * n * 32, st));
+  PB_CUDA(cudaMemcpy2DAsync(cols, n * 32, selectors, constraints * 32, constraints * 32, 11, cudaMemcpyHostToDevice, st));
+  // sigma permutation on the host (composer/permutation.rs:106-141), Lagrange values on the device
+  {
+    std::vector<std::vector<uint64_t>> wmap(n_witnesses);
+    for (size_t g = 0; g < constraints; g++)
+      for (int k = 0; k < 4; k++) {
+        const uint32_t w = wires[(size_t)k * constraints + g];
+        if (w >= n_witnesses) {
+          return fail(PB200_ERR_INVALID_ARG, "wire index out of range");
+        }
+        wmap[w].push_back(((uint64_t)k << 40) | g);
+      }
+    std::vector<unsigned long long> sig(4 * n);
+    for (int k = 0; k < 4; k++)
+      for (size_t i = 0; i < n; i++) sig[(size_t)k * n + i] = ((uint64_t)k << 40) | i;
+    for (auto& lst : wmap)
+      for (size_t i = 0; i < lst.size(); i++) {
+        const uint64_t cur = lst[i], nxt = lst[(i + 1) % lst.size()];
+        sig[(size_t)(cur >> 40) * n + (cur & 0xffffffffffull)] = nxt;
+      }
+    unsigned long long* d_sig = nullptr;
+    PB_CUDA(cudaMallocAsync((void**)&d_sig, 4 * n * 8, st));
+    PB_CUDA(cudaMemcpyAsync(d_sig, sig.data(), 4 * n * 8, cudaMemcpyHostToDevice, st));
+    const uint4* w_half = nullptr;
+    PB_TRY(get_twiddles(log_n, false, st, &w_half));
+    PB_LAUNCH(k_sigma_lagrange, div_up(4 * n, 256), 256, 0, st, d_sig, n, w_half, cols + 2 * (size_t)S1 * n);
+    PB_CUDA(cudaStreamSynchronize(st));  // sig (host vector) must outlive the copy
+    cudaFreeAsync(d_sig, st);
+  }
+  PB_TRY(ntt_run((const uint64_t*)cols, n, (uint64_t*)P->d_polys, log_n, 1, 0, N_POLY, n, n, st));
+  // commitments (compiler.rs:213-232): an all-zero selector commits to the identity
+  {
+    std::vector<uint64_t> aff((size_t)N_POLY * 12);
+    PB_TRY(msm_run(P->srs, 0, (const uint64_t*)P->d_polys, n, N_POLY, n, aff.data(), st));
+    for (int k = 0; k < N_POLY; k++) compress_affine(aff.data() + 12 * k, P->comm[k]);
+    const int widget_sel[4] = {Q_RANGE, Q_LOGIC, Q_FIXED, Q_VAR};
+    for (int w = 0; w < 4; w++) P->has_widget[w] = (P->comm[widget_sel[w]][0] & 0x40) ? 0 : 1;
+  }
+  // coset evaluations over 8n (compiler.rs:306-377)
+  PB_TRY(ntt_run((const uint64_t*)P->d_polys, n, (uint64_t*)P->d_key8, log_n + 3, 0, 1, N_POLY, n, n8, st));
+  {
+    HFr lin[2] = {HFr::zero(), HFr::one()};
+    uint4* d_lin = nullptr;
+    PB_CUDA(cudaMallocAsync((void**)&d_lin, 64, st));
+    PB_CUDA(cudaMemcpyAsync(d_lin, lin, 64, cudaMemcpyHostToDevice, st));
+    PB_TRY(ntt_run((const uint64_t*)d_lin, 2, (uint64_t*)P->d_linear8, log_n + 3, 0, 1, 1, 2, n8, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    cudaFreeAsync(d_lin, st);
+  }
+  // vanishing polynomial on the coset has period 8 (domain.rs:340-351); its inverses are cached
+  // (prover.rs:78-91).  L_1 on the coset: vh[i] * (8 / 8n) / (x_i - 1)  (quotient_poly.rs:265-284).
+  {
+    const HFr g = to_host(ntt_coset_gen(false)), w8n = to_host(ntt_group_gen(log_n + 3, false));
+    HFr point = hfr_pow(g, n), step = hfr_pow(w8n, n);
+    const HFr psi = to_host(ntt_size_inv(log_n + 3)) * HFr::from_u64(8);
+    Period8 c;
+    for (int i = 0; i < 8; i++) {
+      const HFr vh = point - HFr::one();
+      P->vh_inv[i] = vh.inv();
+      c.c[i] = to_dev(vh * psi);
+      point = point * step;
+    }
+    PB_CUDA(cudaMemcpyAsync(P->d_l1_8, P->d_linear8, n8 * 32, cudaMemcpyDeviceToDevice, st));
+    PB_LAUNCH(k_sub_one, div_up(n8, 256), 256, 0, st, P->d_l1_8, n8);
+    PB_LAUNCH(k_batch_div, div_up(div_up(n8, 8), 128), 128, 0, st, (const uint4*)nullptr, (const uint4*)P->d_l1_8, n8, P->d_l1_8);
+    PB_LAUNCH(k_scale_period8, div_up(n8, 256), 256, 0, st, P->d_l1_8, n8, c);
+  }
+  // sigma evaluations over n (prover.rs:95-100)
+  PB_TRY(ntt_run((const uint64_t*)(P->d_polys + 2 * (size_t)S1 * n), n, (uint64_t*)P->d_sigma, log_n, 0, 0, 4, n, n, st));
+  PB_CUDA(cudaGetLastError());
+  PB_CUDA(cudaStreamSynchronize(st));
+  cudaFreeAsync(cols, st);
+  *out = P;
+  return 0;
+}
+
+void prover_free(pb200_prover* P) {
+  if (!P) return;
+  if (P->srs) srs_free(P->srs);
+  cudaFree(P->d_wires); cudaFree(P->d_polys); cudaFree(P->d_key8); cudaFree(P->d_linear8); cudaFree(P->d_l1_8); cudaFree(P->d_sigma);
+  delete P;
+}
+
+static pbh::Transcript base_transcript(const pb200_prover* P) {  // transcript.rs:131-145, widget.rs:218-257
+  pbh::Transcript tr(P->label.data(), P->label.size());
+  tr.circuit_domain_sep(P->constraints);
+  static const char* lbl[N_POLY] = {"q_m", "q_l", "q_r", "q_o", "q_c", "q_f", "q_arith", "q_range", "q_logic",
+                                    "q_variable_group_add", "q_fixed_group_add", "s_sigma_1", "s_sigma_2", "s_sigma_3", "s_sigma_4"};
+  static const int ord[N_POLY] = {Q_M, Q_L, Q_R, Q_O, Q_C, Q_F, Q_ARITH, Q_RANGE, Q_LOGIC, Q_VAR, Q_FIXED, S1, S2, S3, S4};
+  for (int i = 0; i < N_POLY; i++) tr.append_commitment(lbl[i], P->comm[ord[i]]);
+  tr.circuit_domain_sep(P->constraints);
+  return tr;
+}
+
+// Prover::prove_inner, V3.  d_wit: n_witnesses Fr on the device; pi_*: host.
+int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_idx, const uint64_t* pi_vals, size_t n_pi,
+              const uint64_t* blinders_host, uint8_t* out_proof, cudaStream_t st) {
+  const size_t n = P->n, n8 = P->n8, stride = n + 8;
+  const int log_n = P->log_n;
+  const HFr* BL = (const HFr*)blinders_host;
+  pbh::Transcript tr = base_transcript(P);
+  const HFr* PIV = (const HFr*)pi_vals;
+  for (size_t i = 0; i < n_pi; i++) {
+    if (pi_idx[i] >= P->constraints) return fail(PB200_ERR_INVALID_ARG, "public input index out of range");
+    tr.append_scalar("pi", PIV[i]);
+  }
+  const uint4* w_half = nullptr;
+  PB_TRY(get_twiddles(log_n, false, st, &w_half));
+
+  // workspace
+  uint4 *wv, *wp, *zp, *num, *den, *w8, *quot, *tcoef, *tq, *pi_dense, *agg, *pw, *scratch, *evals_d, *partial;
+  unsigned* flag;
+  const unsigned eval_blocks = div_up(stride, 2048);
+  PB_CUDA(cudaMallocAsync((void**)&wv, 4 * n * 32, st));
+  PB_CUDA(cudaMallocAsync((void**)&wp, 4 * stride * 32, st));
+  PB_CUDA(cudaMallocAsync((void**)&zp, stride * 32, st));
+  PB_CUDA(cudaMallocAsync((void**)&num, n * 32, st));
+  PB_CUDA(cudaMallocAsync((void**)&den, n * 32, st));
+  PB_CUDA(cudaMallocAsync((void**)&w8, 6 * n8 * 32, st));
+  PB_CUDA(cudaMallocAsync((void**)&quot, n8 * 32, st));
+  PB_CUDA(cudaMallocAsync((void**)&tcoef, n8 * 32, st));
+  PB_CUDA(cudaMallocAsync((void**)&tq, 4 * stride * 32, st));
+  PB_CUDA(cudaMallocAsync((void**)&pi_dense, 2 * n * 32, st));
+  PB_CUDA(cudaMallocAsync((void**)&agg, 2 * stride * 32, st));
+  PB_CUDA(cudaMallocAsync((void**)&pw, 2 * stride * 32, st));
+  PB_CUDA(cudaMallocAsync((void**)&scratch, 2 * stride * 32, st));
+  PB_CUDA(cudaMallocAsync((void**)&evals_d, 16 * 32, st));
+  PB_CUDA(cudaMallocAsync((void**)&partial, (size_t)16 * eval_blocks * 32, st));
+  PB_CUDA(cudaMallocAsync((void**)&flag, 4, st));
+  auto free_all = [&]() {
+    uint4* bufs[] = {wv, wp, zp, num, den, w8, quot, tcoef, tq, pi_dense, agg, pw, scratch, evals_d, partial};
+    for (uint4* b : bufs) cudaFreeAsync(b, st);
+    cudaFreeAsync(flag, st);
+  };
+  struct Guard {
+    decltype(free_all)& f;
+    ~Guard() { f(); }
+  } guard{free_all};
+
+  uint64_t aff[4 * 12];
+  uint8_t c48[11][48];
+
+  // ---- round 1 -------------------------------------------------------------------------------
+  PB_LAUNCH(k_gather_wires, dim3(div_up(n, 256), 4), 256, 0, st, (const uint4*)d_wit, (const uint32_t*)P->d_wires, P->constraints, n, wv);
+  PB_CUDA(cudaMemsetAsync(wp, 0, 4 * stride * 32, st));
+  PB_TRY(ntt_run((const uint64_t*)wv, n, (uint64_t*)wp, log_n, 1, 0, 4, n, stride, st));
+  {
+    BlindArgs ba;
+    ba.nb = 2;
+    ba.npoly = 4;
+    for (int p = 0; p < 4; p++)
+      for (int i = 0; i < 2; i++) ba.b[p][i] = to_dev(BL[2 * p + i]);
+    PB_LAUNCH(k_blind, 1, 32, 0, st, wp, stride, n, ba);
+  }
+  PB_TRY(msm_run(P->srs, 0, (const uint64_t*)wp, n + 2, 4, stride, aff, st));
+  for (int k = 0; k < 4; k++) compress_affine(aff + 12 * k, c48[k]);
+  tr.append_commitment("a_comm", c48[0]);
+  tr.append_commitment("b_comm", c48[1]);
+  tr.append_commitment("c_comm", c48[2]);
+  tr.append_commitment("d_comm", c48[3]);
+
+  // ---- round 2 -------------------------------------------------------------------------------
+  const HFr beta = tr.challenge_scalar("beta");
+  tr.append_scalar("beta", beta);
+  const HFr gamma = tr.challenge_scalar("gamma");
+  PB_LAUNCH(k_perm_terms, div_up(n, 128), 128, 0, st, (const uint4*)wv, (const uint4*)P->d_sigma, w_half, n, to_dev(beta), to_dev(gamma), num, den);
+  PB_LAUNCH(k_batch_div, div_up(div_up(n, 8), 128), 128, 0, st, (const uint4*)num, (const uint4*)den, n, num);
+  PB_TRY((fr_scan<true, false>(num, n, den, st)));  // den <- permutation vector z[i] = prod_{j<i} num_j/den_j
+  PB_CUDA(cudaMemsetAsync(zp, 0, stride * 32, st));
+  PB_TRY(ntt_run((const uint64_t*)den, n, (uint64_t*)zp, log_n, 1, 0, 1, n, stride, st));
+  {
+    BlindArgs ba;
+    ba.nb = 3;
+    ba.npoly = 1;
+    for (int i = 0; i < 3; i++) ba.b[0][i] = to_dev(BL[8 + i]);
+    PB_LAUNCH(k_blind, 1, 32, 0, st, zp, stride, n, ba);
+  }
+  PB_TRY(msm_run(P->srs, 0, (const uint64_t*)zp, n + 3, 1, stride, aff, st));
+  compress_affine(aff, c48[4]);
+  tr.append_commitment("z_comm", c48[4]);
+
+  // ---- round 3 -------------------------------------------------------------------------------
+  const HFr alpha = tr.challenge_scalar("alpha");
+  const HFr ch_range = tr.challenge_scalar("range separation challenge");
+  const HFr ch_logic = tr.challenge_scalar("logic separation challenge");
+  const HFr ch_fixed = tr.challenge_scalar("fixed base separation challenge");
+  const HFr ch_var = tr.challenge_scalar("variable base separation challenge");
+  // public-input polynomial (prover.rs:519-521)
+  PB_CUDA(cudaMemsetAsync(pi_dense, 0, 2 * n * 32, st));
+  for (size_t i = 0; i < n_pi; i++)
+    PB_CUDA(cudaMemcpyAsync(pi_dense + 2 * pi_idx[i], PIV + i, 32, cudaMemcpyHostToDevice, st));
+  if (n_pi) PB_TRY(ntt_run((const uint64_t*)pi_dense, n, (uint64_t*)(pi_dense + 2 * n), log_n, 1, 0, 1, n, n, st));
+  // coset evaluations: z, a, b, c, d, pi (quotient_poly.rs:50-59, 177)
+  PB_TRY(ntt_run((const uint64_t*)zp, n + 3, (uint64_t*)w8, log_n + 3, 0, 1, 1, stride, n8, st));
+  PB_TRY(ntt_run((const uint64_t*)wp, n + 2, (uint64_t*)(w8 + 2 * n8), log_n + 3, 0, 1, 4, stride, n8, st));
+  PB_TRY(ntt_run((const uint64_t*)(pi_dense + 2 * n), n_pi ? n : 0, (uint64_t*)(w8 + 2 * 5 * n8), log_n + 3, 0, 1, 1, n, n8, st));
+  {
+    QuotArgs q;
+    q.w8 = w8; q.key8 = P->d_key8; q.linear8 = P->d_linear8; q.l1_8 = P->d_l1_8; q.out = quot; q.n8 = n8;
+    q.alpha = to_dev(alpha); q.beta = to_dev(beta); q.gamma = to_dev(gamma); q.alpha_sq = to_dev(alpha.sqr());
+    q.ch_range = to_dev(ch_range); q.ch_logic = to_dev(ch_logic); q.ch_fixed = to_dev(ch_fixed); q.ch_var = to_dev(ch_var);
+    for (int i = 0; i < 8; i++) q.vh_inv[i] = to_dev(P->vh_inv[i]);
+    q.has_range = P->has_widget[0]; q.has_logic = P->has_widget[1]; q.has_fixed = P->has_widget[2]; q.has_var = P->has_widget[3];
+    PB_LAUNCH(k_quotient, div_up(n8, 128), 128, 0, st, q);
+  }
+  PB_TRY(ntt_run((const uint64_t*)quot, n8, (uint64_t*)tcoef, log_n + 3, 1, 1, 1, n8, n8, st));
+  // quotient_poly.len() > 7n  =>  CircuitUnsatisfied (quotient_poly.rs:132-134); coefficients past
+  // 4n+7 cannot be committed with this key either
+  PB_CUDA(cudaMemsetAsync(flag, 0, 4, st));
+  PB_LAUNCH(k_any_nonzero, div_up(n8 - 7 * n, 256), 256, 0, st, (const uint4*)tcoef, 7 * n, n8, flag);
+  PB_LAUNCH(k_split_quotient, dim3(div_up(stride, 256), 4), 256, 0, st, (const uint4*)tcoef, n, n8, stride, to_dev(BL[11]), to_dev(BL[12]), to_dev(BL[13]), tq);
+  unsigned h_flag = 0;
+  PB_CUDA(cudaMemcpyAsync(&h_flag, flag, 4, cudaMemcpyDeviceToHost, st));
+  const size_t key_len = srs_len(P->srs);
+  const size_t tlen = std::min(stride, key_len);
+  PB_TRY(msm_run(P->srs, 0, (const uint64_t*)tq, tlen, 4, stride, aff, st));  // synchronises the stream
+  if (h_flag) return fail(PB200_ERR_UNSATISFIED, "CircuitUnsatisfied");
+  for (int k = 0; k < 4; k++) compress_affine(aff + 12 * k, c48[5 + k]);
+  tr.append_commitment("t_low_comm", c48[5]);
+  tr.append_commitment("t_mid_comm", c48[6]);
+  tr.append_commitment("t_high_comm", c48[7]);
+  tr.append_commitment("t_fourth_comm", c48[8]);
+
+  // ---- round 4 -------------------------------------------------------------------------------
+  const HFr z_ch = tr.challenge_scalar("z_challenge");
+  const HFr zw = z_ch * to_host(ntt_group_gen(log_n, false));
+  enum { E_A, E_B, E_C, E_D, E_AW, E_BW, E_DW, E_QARITH, E_QC, E_QL, E_QR, E_S1, E_S2, E_S3, E_Z };
+  HFr ev[15];
+  {
+    EvalJobs jobs;
+    jobs.njobs = 15;
+    auto poly = [&](int k) { return (const uint4*)(P->d_polys + 2 * (size_t)k * n); };
+    const uint4* ps[15] = {wp, wp + 2 * stride, wp + 4 * stride, wp + 6 * stride, wp, wp + 2 * stride, wp + 6 * stride,
+                           poly(Q_ARITH), poly(Q_C), poly(Q_L), poly(Q_R), poly(S1), poly(S2), poly(S3), zp};
+    const unsigned ls[15] = {(unsigned)n + 2, (unsigned)n + 2, (unsigned)n + 2, (unsigned)n + 2, (unsigned)n + 2, (unsigned)n + 2, (unsigned)n + 2,
+                             (unsigned)n, (unsigned)n, (unsigned)n, (unsigned)n, (unsigned)n, (unsigned)n, (unsigned)n, (unsigned)n + 3};
+    const bool shifted[15] = {0, 0, 0, 0, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 1};
+    for (int j = 0; j < 15; j++) {
+      jobs.poly[j] = ps[j];
+      jobs.len[j] = ls[j];
+      jobs.point[j] = to_dev(shifted[j] ? zw : z_ch);
+    }
+    PB_LAUNCH(k_poly_eval, dim3(eval_blocks, 15), 256, 0, st, jobs, partial, eval_blocks);
+    PB_LAUNCH(k_sum_rows, 15, 32, 0, st, (const uint4*)partial, eval_blocks, evals_d);
+    PB_CUDA(cudaMemcpyAsync(ev, evals_d, 15 * 32, cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+  }
+  tr.append_scalar("a_eval", ev[E_A]); tr.append_scalar("b_eval", ev[E_B]); tr.append_scalar("c_eval", ev[E_C]); tr.append_scalar("d_eval", ev[E_D]);
+  tr.append_scalar("s_sigma_1_eval", ev[E_S1]); tr.append_scalar("s_sigma_2_eval", ev[E_S2]); tr.append_scalar("s_sigma_3_eval", ev[E_S3]);
+  tr.append_scalar("z_eval", ev[E_Z]);
+  tr.append_scalar("a_w_eval", ev[E_AW]); tr.append_scalar("b_w_eval", ev[E_BW]); tr.append_scalar("d_w_eval", ev[E_DW]);
+  tr.append_scalar("q_arith_eval", ev[E_QARITH]); tr.append_scalar("q_c_eval", ev[E_QC]); tr.append_scalar("q_l_eval", ev[E_QL]); tr.append_scalar("q_r_eval", ev[E_QR]);
+
+  // ---- round 5 -------------------------------------------------------------------------------
+  const HFr v = tr.challenge_scalar("v_challenge");
+  const HFr v_w = tr.challenge_scalar("v_w_challenge");  // nothing is appended in between (prover.rs:680-730)
+  {
+    // host-side widget scalars of the linearisation polynomial (all widget compute_linearization)
+    auto h4 = [](const HFr& x) { return x.dbl().dbl(); };
+    auto delta = [](const HFr& f) { HFr o = HFr::one(); HFr f1 = f - o, f2 = f1 - o, f3 = f2 - o; return f * f1 * f2 * f3; };
+    auto small = [](uint64_t k) { return HFr::from_u64(k); };
+    const HFr &a = ev[E_A], &b = ev[E_B], &c = ev[E_C], &d = ev[E_D], &a_w = ev[E_AW], &b_w = ev[E_BW], &d_w = ev[E_DW];
+    HFr s_range, s_logic, s_fixed, s_var;
+    {
+      HFr k = ch_range.sqr(), k2 = k.sqr(), k3 = k2 * k;
+      s_range = (delta(c - h4(d)) + delta(b - h4(c)) * k + delta(a - h4(b)) * k2 + delta(d_w - h4(a)) * k3) * ch_range;
+    }
+    {
+      HFr k = ch_logic.sqr(), k2 = k.sqr(), k3 = k2 * k, k4 = k3 * k;
+      HFr A = a_w - h4(a), B = b_w - h4(b), D = d_w - h4(d);
+      const HFr& w = c;
+      HFr F = w * (w * (h4(w) - small(18) * (A + B) + small(81)) + small(18) * (A.sqr() + B.sqr()) - small(81) * (A + B) + small(83));
+      HFr E = small(3) * (A + B + D) - F.dbl();
+      HFr Bq = ev[E_QC] * (small(9) * D - small(3) * (A + B));
+      s_logic = (delta(A) + delta(B) * k + delta(D) * k2 + (w - A * B) * k3 + (Bq + E) * k4) * ch_logic;
+    }
+    const HFr ed = (small(10240) * small(10241).inv()).neg();
+    {
+      HFr one = HFr::one(), k = ch_fixed.sqr(), k2 = k.sqr(), k3 = k2 * k;
+      HFr bit = d_w - d - d;
+      HFr bit_c = bit * (bit - one) * (bit + one);
+      HFr y_alpha = bit.sqr() * (ev[E_QR] - one) + one, x_alpha = bit * ev[E_QL];
+      HFr xy = (bit * ev[E_QC] - c) * k;
+      HFr t = c * a * b * ed;
+      HFr xa = ((a_w + a_w * t) - (a * y_alpha + b * x_alpha)) * k2;
+      HFr ya = ((b_w - b_w * t) - (b * y_alpha + a * x_alpha)) * k3;
+      s_fixed = (bit_c + xa + ya + xy) * ch_fixed;
+    }
+    {
+      HFr k = ch_var.sqr();
+      HFr xy = a * d - d_w, y1x2 = b * c, y1y2 = b * d, x1x2 = a * c;
+      HFr t = ed * d_w * y1x2;
+      HFr x3c = ((d_w + y1x2) - (a_w + a_w * t)) * k;
+      HFr y3c = ((y1y2 + x1x2) - (b_w - b_w * t)) * k.sqr();
+      s_var = (xy + x3c + y3c) * ch_var;
+    }
+    const HFr bz = beta * z_ch;
+    const HFr s_ident = (a + bz + gamma) * (b + small(7) * bz + gamma) * (c + small(13) * bz + gamma) * (d + small(17) * bz + gamma) * alpha;
+    const HFr s_copy = (a + beta * ev[E_S1] + gamma) * (b + beta * ev[E_S2] + gamma) * (c + beta * ev[E_S3] + gamma) * (beta * ev[E_Z]) * alpha;
+    const HFr z_n = hfr_pow(z_ch, n);
+    // domain of z_poly.degree() - 2 is the proving domain n (permutation/proverkey.rs:156-163)
+    const HFr l1_z = (z_n - HFr::one()) * to_host(ntt_size_inv(log_n)) * (z_ch - HFr::one()).inv();
+    const HFr zh = (z_n - HFr::one()).neg();
+    HFr vp[12];
+    vp[0] = HFr::one();
+    for (int i = 1; i < 12; i++) vp[i] = vp[i - 1] * v;
+    auto poly = [&](int k) { return (const uint4*)(P->d_polys + 2 * (size_t)k * n); };
+    const HFr qa = ev[E_QARITH];
+    // W_z numerator: r + v a + v^2 b + v^3 c + v^4 d + v^5 s1 + v^6 s2 + v^7 s3 + v^8 q_arith + v^9 q_c + v^10 q_l + v^11 q_r
+    LinArgs la;
+    int t = 0;
+    auto term = [&](const uint4* p, size_t len, const HFr& coef) { la.poly[t] = p; la.len[t] = (unsigned)len; la.coef[t] = to_dev(coef); t++; };
+    term(poly(Q_M), n, a * b * qa);
+    term(poly(Q_L), n, a * qa + vp[10]);
+    term(poly(Q_R), n, b * qa + vp[11]);
+    term(poly(Q_O), n, c * qa);
+    term(poly(Q_F), n, d * qa);
+    term(poly(Q_C), n, qa + vp[9]);
+    term(poly(Q_ARITH), n, vp[8]);
+    term(poly(Q_RANGE), n, s_range);
+    term(poly(Q_LOGIC), n, s_logic);
+    term(poly(Q_FIXED), n, s_fixed);
+    term(poly(Q_VAR), n, s_var);
+    term(zp, n + 3, s_ident + l1_z * alpha.sqr());
+    term(poly(S4), n, s_copy.neg());
+    term(tq, stride, zh);
+    term(tq + 2 * stride, stride, zh * z_n);
+    term(tq + 4 * stride, stride, zh * z_n.sqr());
+    term(tq + 6 * stride, stride, zh * z_n.sqr() * z_n);
+    term(wp, n + 2, vp[1]);
+    term(wp + 2 * stride, n + 2, vp[2]);
+    term(wp + 4 * stride, n + 2, vp[3]);
+    term(wp + 6 * stride, n + 2, vp[4]);
+    term(poly(S1), n, vp[5]);
+    term(poly(S2), n, vp[6]);
+    term(poly(S3), n, vp[7]);
+    la.nterms = t;
+    PB_LAUNCH(k_lincomb, div_up(stride, 128), 128, 0, st, la, stride, agg);
+    // W_zw numerator: z + v_w a + v_w^2 b + v_w^3 d
+    LinArgs lb;
+    t = 0;
+    auto term2 = [&](const uint4* p, size_t len, const HFr& coef) { lb.poly[t] = p; lb.len[t] = (unsigned)len; lb.coef[t] = to_dev(coef); t++; };
+    term2(zp, n + 3, HFr::one());
+    term2(wp, n + 2, v_w);
+    term2(wp + 2 * stride, n + 2, v_w.sqr());
+    term2(wp + 6 * stride, n + 2, v_w.sqr() * v_w);
+    lb.nterms = t;
+    PB_LAUNCH(k_lincomb, div_up(stride, 128), 128, 0, st, lb, stride, agg + 2 * stride);
+    // ruffini (polynomial.rs:345-367): q_j = z^-(j+1) * sum_{i>j} c_i z^i
+    const HFr pts[2] = {z_ch, zw};
+    for (int w = 0; w < 2; w++) {
+      uint4* c_w = agg + 2 * (size_t)w * stride;
+      uint4* pw_w = pw + 2 * (size_t)w * stride;
+      uint4* sc_w = scratch + 2 * (size_t)w * stride;
+      PB_TRY(fill_powers(pw_w, stride, to_dev(pts[w]), Fr::one(), st));
+      PB_LAUNCH(k_mul_pointwise, div_up(stride, 128), 128, 0, st, (const uint4*)c_w, (const uint4*)pw_w, stride, sc_w);
+      PB_TRY((fr_scan<false, true>(sc_w, stride, c_w, st)));  // exclusive suffix sums
+      const HFr zi = pts[w].inv();
+      PB_TRY(fill_powers(pw_w, stride, to_dev(zi), to_dev(zi), st));
+      PB_LAUNCH(k_mul_pointwise, div_up(stride, 128), 128, 0, st, (const uint4*)c_w, (const uint4*)pw_w, stride, c_w);
+    }
+    const size_t wlen = std::min(stride, key_len);
+    PB_TRY(msm_run(P->srs, 0, (const uint64_t*)agg, wlen, 2, stride, aff, st));
+    compress_affine(aff, c48[9]);
+    compress_affine(aff + 12, c48[10]);
+  }
+  // Proof::to_bytes (proof.rs:137-162, linearization_poly.rs:98-124)
+  for (int i = 0; i < 11; i++) memcpy(out_proof + 48 * i, c48[i], 48);
+  for (int i = 0; i < 15; i++) {
+    HFr cnon = ev[i].from_mont();
+    memcpy(out_proof + 528 + 32 * i, cnon.v, 32);
+  }
+  return 0;
+}
+
+}  // namespace pb
+
+using namespace pb;
+
+extern "C" {
+
+int pb200_prover_new(const uint8_t* label, size_t label_len, size_t n_constraints, const uint64_t* selectors,
+                     const uint32_t* wires, size_t n_witnesses, const uint8_t* srs_raw, size_t n_srs_points,
+                     pb200_prover_t** out) {
+  PB_TRY(ensure_init());
+  if (!selectors || !wires || !srs_raw || !out) return fail(PB200_ERR_INVALID_ARG, "null argument");
+  return prover_new(label, label_len, n_constraints, selectors, wires, n_witnesses, srs_raw, n_srs_points, out);
+}
+
+void pb200_prover_free(pb200_prover_t* p) { prover_free(p); }
+
+int pb200_prover_commitments(const pb200_prover_t* p, uint8_t* out /* 15 x 48 */) {
+  if (!p || !out) return fail(PB200_ERR_INVALID_ARG, "null argument");
+  memcpy(out, p->comm, sizeof p->comm);
+  return 0;
+}
+
+int pb200_prove(const pb200_prover_t* p, const uint64_t* witnesses, size_t n_witnesses, const uint64_t* pi_idx,
+                const uint64_t* pi_vals, size_t n_pi, const uint64_t* blinders, uint8_t* out_proof) {
+  PB_TRY(ensure_init());
+  if (!p || !witnesses || !blinders || !out_proof) return fail(PB200_ERR_INVALID_ARG, "null argument");
+  if (n_witnesses != p->n_witnesses) return fail(PB200_ERR_INVALID_ARG, "witness count differs from the compiled circuit");
+  cudaStream_t st = thread_stream();
+  uint64_t* d_wit = nullptr;
+  PB_CUDA(cudaMallocAsync((void**)&d_wit, n_witnesses * 32, st));
+  PB_CUDA(cudaMemcpyAsync(d_wit, witnesses, n_witnesses * 32, cudaMemcpyHostToDevice, st));
+  int rc = prove_dev(p, d_wit, pi_idx, pi_vals, n_pi, blinders, out_proof, st);
+  cudaFreeAsync(d_wit, st);
+  return rc;
+}
+
+int pb200_prove_dev(const pb200_prover_t* p, const uint64_t* d_witnesses, const uint64_t* pi_idx, const uint64_t* pi_vals,
+                    size_t n_pi, const uint64_t* blinders, uint8_t* out_proof, void* stream) {
+  PB_TRY(ensure_init());
+  if (!p || !d_witnesses || !blinders || !out_proof) return fail(PB200_ERR_INVALID_ARG, "null argument");
+  cudaStream_t st = stream ? (cudaStream_t)stream : thread_stream();
+  return prove_dev(p, d_witnesses, pi_idx, pi_vals, n_pi, blinders, out_proof, st);
+}
+}
