@@ -1,10 +1,18 @@
 #!/bin/bash
-# Builds libplonk_b200.so (sm_100a) in-tree.  Usage: ./build.sh [extra nvcc flags]
+# Builds libplonk_b200.so (sm_100a) in-tree; translation units compile in parallel.
 set -e
 cd "$(dirname "$0")"
 SRC=plonk_b200/csrc
 OUT=plonk_b200/libplonk_b200.so
-nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a \
-     -Xcompiler -fPIC -Xcompiler -O2 -shared "$@" \
-     -o "$OUT" $SRC/capi.cu $SRC/ntt.cu $SRC/msm.cu $SRC/host_field.cpp $(ls $SRC/prover*.cu 2>/dev/null) -lcudart
+OBJ=build/obj
+mkdir -p $OBJ
+NVFLAGS="-std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xcompiler -O2 $*"
+pids=()
+for f in capi ntt msm prover; do
+  nvcc $NVFLAGS -c -o $OBJ/$f.o $SRC/$f.cu &
+  pids+=($!)
+done
+g++ -std=c++17 -O2 -fPIC -c -o $OBJ/host_field.o $SRC/host_field.cpp
+for p in "${pids[@]}"; do wait $p; done
+nvcc -shared -o "$OUT" $OBJ/capi.o $OBJ/ntt.o $OBJ/msm.o $OBJ/prover.o $OBJ/host_field.o -lcudart
 echo "built $OUT"

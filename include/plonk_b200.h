@@ -88,6 +88,11 @@ int pb200_msm_g1_dev(const pb200_srs_t* srs, const uint64_t* d_scalars, size_t n
 int pb200_msm_g1_range(const pb200_srs_t* srs, size_t first, const uint64_t* scalars,
                        size_t n_scalars, uint64_t* out_affine);
 
+/* PublicParameters::setup with explicit secrets (srs.rs:61-100): out[i] = [g_scalar * x^i] G1, as
+ * n_points x 96-byte raw points.  Test/bench helper - a real SRS comes from a ceremony. */
+int pb200_srs_setup_from_secret(const uint64_t* x, const uint64_t* g_scalar, size_t n_points,
+                                uint8_t* out_raw);
+
 /* 48-byte compressed encoding of one affine point given in the 96-byte raw layout. */
 int pb200_g1_compress(const uint64_t* affine_raw, uint8_t out48[48]);
 /* out = a + b for two points in the 96-byte raw layout (host-side helper for multi-GPU reduction). */
@@ -124,6 +129,12 @@ int pb200_prove_dev(const pb200_prover_t* prover, const uint64_t* d_witnesses,
                     const uint64_t* blinders, uint8_t* out_proof, void* stream);
 
 /* ---- measurement helpers ----------------------------------------------------------------- */
+/* In-library CUDA-event timing of the MSM bucket-accumulation kernel (the dominant kernel of a
+ * proof) on its launching stream: enable resets the counters; read returns the summed kernel time,
+ * the G1 mixed additions it executed, its launch count and the MSM points processed. */
+int pb200_profile_enable(int on);
+int pb200_profile_read(double* accumulate_ms, uint64_t* accumulate_adds, uint64_t* accumulate_launches,
+                       uint64_t* msm_points);
 /* Register-only IMAD.WIDE microbenchmark: returns achieved 32x32+64 multiply-adds per second. */
 int pb200_imad_peak(double* mads_per_sec);
 /* Elementwise Fr / Fp Montgomery products on the device (kernel self-test of the arithmetic). */

@@ -24,7 +24,8 @@ EXPORTS = [
     "pb200_ntt", "pb200_ntt_dev",
     "pb200_srs_upload", "pb200_srs_free", "pb200_srs_len",
     "pb200_msm_g1", "pb200_msm_g1_dev", "pb200_msm_g1_range",
-    "pb200_g1_compress", "pb200_g1_add_affine",
+    "pb200_g1_compress", "pb200_g1_add_affine", "pb200_srs_setup_from_secret",
+    "pb200_profile_enable", "pb200_profile_read",
     "pb200_prover_new", "pb200_prover_free", "pb200_prover_commitments", "pb200_prove", "pb200_prove_dev",
     "pb200_imad_peak", "pb200_selftest_fr_mul", "pb200_selftest_fp_mul",
 ]
@@ -67,6 +68,9 @@ def lib() -> ctypes.CDLL:
         L.pb200_prover_commitments.argtypes = [c.c_void_p, c.c_void_p]
         L.pb200_prove.argtypes = [c.c_void_p, c.c_void_p, c.c_size_t, c.c_void_p, c.c_void_p, c.c_size_t, c.c_void_p, c.c_void_p]
         L.pb200_prove_dev.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_size_t, c.c_void_p, c.c_void_p, c.c_void_p]
+        L.pb200_srs_setup_from_secret.argtypes = [c.c_void_p, c.c_void_p, c.c_size_t, c.c_void_p]
+        L.pb200_profile_enable.argtypes = [c.c_int]
+        L.pb200_profile_read.argtypes = [c.POINTER(c.c_double), c.POINTER(c.c_uint64), c.POINTER(c.c_uint64), c.POINTER(c.c_uint64)]
         L.pb200_imad_peak.argtypes = [c.POINTER(c.c_double)]
         L.pb200_selftest_fr_mul.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_size_t]
         L.pb200_selftest_fp_mul.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_size_t]

@@ -47,6 +47,9 @@ int srs_upload(const uint8_t* raw, size_t n_points, pb200_srs** out);
 int selftest_mul(int which, const uint64_t* a, const uint64_t* b, uint64_t* o, size_t n);
 int imad_peak(double* out);
 size_t srs_len(const pb200_srs* s);
+int srs_setup(const uint64_t* x_mont, const uint64_t* g_scalar_mont, size_t n, uint8_t* out_raw);
+extern std::atomic<int> g_prof_on;
+extern std::atomic<uint64_t> g_prof_acc_ns, g_prof_acc_adds, g_prof_acc_launches, g_prof_acc_points;
 void srs_free(pb200_srs* s);
 }  // namespace pb
 
@@ -181,6 +184,25 @@ int pb200_g1_add_affine(const uint64_t* a_raw, const uint64_t* b_raw, uint64_t* 
   pbh::hxyzz_to_affine(a, &x, &y);
   memcpy(out_raw, x.v, 48);
   memcpy(out_raw + 6, y.v, 48);
+  return 0;
+}
+
+int pb200_srs_setup_from_secret(const uint64_t* x, const uint64_t* g_scalar, size_t n_points, uint8_t* out_raw) {
+  PB_TRY(ensure_init());
+  if (!x || !g_scalar || !out_raw || !n_points) return fail(PB200_ERR_INVALID_ARG, "null argument");
+  return srs_setup(x, g_scalar, n_points, out_raw);
+}
+
+int pb200_profile_enable(int on) {
+  g_prof_acc_ns = 0; g_prof_acc_adds = 0; g_prof_acc_launches = 0; g_prof_acc_points = 0;
+  g_prof_on = on ? 1 : 0;
+  return 0;
+}
+int pb200_profile_read(double* accumulate_ms, uint64_t* accumulate_adds, uint64_t* accumulate_launches, uint64_t* msm_points) {
+  if (accumulate_ms) *accumulate_ms = (double)g_prof_acc_ns.load() * 1e-6;
+  if (accumulate_adds) *accumulate_adds = g_prof_acc_adds.load();
+  if (accumulate_launches) *accumulate_launches = g_prof_acc_launches.load();
+  if (msm_points) *msm_points = g_prof_acc_points.load();
   return 0;
 }
 

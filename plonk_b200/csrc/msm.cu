@@ -21,6 +21,7 @@
 //   * `batch` scalar vectors against the same key are processed by the same launches
 //     (Prover::commit_polynomials commits 4 polynomials at once, src/compiler/prover.rs:187-210).
 #include <algorithm>
+#include <atomic>
 #include <vector>
 
 #include "common.cuh"
@@ -95,6 +96,34 @@ __global__ void k_msm_precompute(uint4* table, size_t n, int c, int W) {
     }
     st_affine(table, (size_t)w * n + i, p);
   }
+}
+
+// PublicParameters::setup restated for the device (reference src/commitment_scheme/kzg10/srs.rs:61-100):
+// out[i] = [g_scalar * x^i] G1::generator, normalised to affine.  One thread per power.
+__global__ void __launch_bounds__(64) k_srs_setup(uint4* out, size_t n, Fr x, Fr g_scalar) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Fr s = (g_scalar * x.pow_u64(i)).from_mont();
+  G1Affine g;
+  const uint32_t gx[12] = {0xfd530c16u, 0x5cb38790u, 0x9976fff5u, 0x7817fc67u, 0x143ba1c1u, 0x154f95c7u,
+                           0xf3d0e747u, 0xf0ae6acdu, 0x21dbf440u, 0xedce6eccu, 0x9e0bfb75u, 0x12017741u};
+  const uint32_t gy[12] = {0x0ce72271u, 0xbaac93d5u, 0x7918fd8eu, 0x8c22631au, 0x570725ceu, 0xdd595f13u,
+                           0x50405194u, 0x51ac5829u, 0xad0059c0u, 0x0e1c8c3fu, 0x5008a26au, 0x0bbc3efcu};
+#pragma unroll
+  for (int k = 0; k < 12; k++) {
+    g.x.v[k] = gx[k];
+    g.y.v[k] = gy[k];
+  }
+  G1Xyzz acc = G1Xyzz::identity();
+#pragma unroll 1
+  for (int w = 7; w >= 0; w--) {
+#pragma unroll 1
+    for (int b = 31; b >= 0; b--) {
+      acc = xyzz_dbl(acc);
+      if ((s.v[w] >> b) & 1u) xyzz_madd(acc, g.x, g.y);
+    }
+  }
+  st_affine(out, i, xyzz_to_affine(acc));
 }
 
 // Signed-digit recoding + bucket histogram.  ebkt/epos are [batch][W][n].
@@ -309,6 +338,11 @@ __global__ void k_imad_peak(unsigned* out, int iters, unsigned seed) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Optional in-library timing of the dominant kernel (bucket accumulation) with CUDA events on the
+// launching stream; read by bench.py for the roofline line.
+std::atomic<int> g_prof_on{0};
+std::atomic<uint64_t> g_prof_acc_ns{0}, g_prof_acc_adds{0}, g_prof_acc_launches{0}, g_prof_acc_points{0};
+
 static int pick_window(size_t n_points) {
   if (const char* env = getenv("PB200_MSM_C")) {
     int c = atoi(env);
@@ -373,8 +407,20 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
   PB_LAUNCH(k_msm_scan, batch, 1024, 0, st, counts, offsets, nb);
   PB_LAUNCH(k_msm_scatter, dim3(div_up(n, 256), W, batch), 256, 0, st, ebkt, epos, offsets, n, W, nb,
             srs->n_points, first, sorted);
+  const bool prof = g_prof_on.load(std::memory_order_relaxed) != 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (prof) {
+    PB_CUDA(cudaEventCreate(&ev0));
+    PB_CUDA(cudaEventCreate(&ev1));
+    PB_CUDA(cudaEventRecord(ev0, st));
+  }
   PB_LAUNCH(k_msm_accumulate, dim3(div_up((size_t)nb << log_split, 128), batch), 128, 0, st, srs->table, sorted,
             offsets, nb, log_split, cap, partial);
+  std::vector<unsigned> h_tot(batch, 0);
+  if (prof) {
+    PB_CUDA(cudaEventRecord(ev1, st));
+    PB_CUDA(cudaMemcpy2DAsync(h_tot.data(), 4, offsets + nb, (size_t)(nb + 1) * 4, 4, batch, cudaMemcpyDeviceToHost, st));
+  }
   PB_LAUNCH(k_msm_groups, dim3(div_up(n_groups, 64), batch), 64, 0, st, partial, nb, log_split, g, S, A);
   PB_LAUNCH(k_msm_class_sums, dim3(div_up(n1, 64), nbits + 1, batch), 64, 0, st, S, A, n_groups, nbits, n1, t0);
   unsigned cur = n1;
@@ -389,6 +435,19 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
   std::vector<uint32_t> host((size_t)rows * cur * 48);
   PB_CUDA(cudaMemcpyAsync(host.data(), src, host.size() * 4, cudaMemcpyDeviceToHost, st));
   PB_CUDA(cudaStreamSynchronize(st));
+  if (prof) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) {
+      uint64_t adds = 0;
+      for (unsigned t : h_tot) adds += t;
+      g_prof_acc_ns.fetch_add((uint64_t)(ms * 1e6));
+      g_prof_acc_adds.fetch_add(adds);
+      g_prof_acc_points.fetch_add((uint64_t)n * batch);
+      g_prof_acc_launches.fetch_add(1);
+    }
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+  }
   cudaFreeAsync(counts, st); cudaFreeAsync(offsets, st); cudaFreeAsync(ebkt, st); cudaFreeAsync(epos, st);
   cudaFreeAsync(sorted, st); cudaFreeAsync(partial, st); cudaFreeAsync(S, st); cudaFreeAsync(A, st);
   cudaFreeAsync(t0, st); cudaFreeAsync(t1, st);
@@ -446,6 +505,20 @@ int srs_upload(const uint8_t* raw, size_t n_points, pb200_srs** out) {
     return fail(PB200_ERR_CUDA, "commit key upload", cudaGetErrorString(e));
   }
   *out = s;
+  return 0;
+}
+
+int srs_setup(const uint64_t* x_mont, const uint64_t* g_scalar_mont, size_t n, uint8_t* out_raw) {
+  cudaStream_t st = thread_stream();
+  uint4* d = nullptr;
+  PB_CUDA(cudaMalloc((void**)&d, n * 96));
+  Fr x, gs;
+  memcpy(x.v, x_mont, 32);
+  memcpy(gs.v, g_scalar_mont, 32);
+  PB_LAUNCH(k_srs_setup, div_up(n, 64), 64, 0, st, d, n, x, gs);
+  PB_CUDA(cudaMemcpyAsync(out_raw, d, n * 96, cudaMemcpyDeviceToHost, st));
+  PB_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d);
   return 0;
 }
 

@@ -1,0 +1,79 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed).
+
+The prover path shards by independent proofs (no data-path collective).  The
+only exchange step is the one a single large MSM needs when its points are partitioned across GPUs
+(section 8e-ii, BASELINE.json configs[3]): every rank reduces its contiguous slice of the commit key
+to one G1 point, the 96-byte results are all-gathered (NCCL over NVLink on GPUs, gloo in the CPU
+tests) and each rank adds them locally - EC addition is not an NCCL reduction op."""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Tuple
+
+from ._lib import check, lib
+
+G1_RAW_BYTES = 96
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [first, first+count) slice of n items for `rank`; sizes differ by at most one."""
+    base, extra = divmod(n, world)
+    first = rank * base + min(rank, extra)
+    return first, base + (1 if rank < extra else 0)
+
+
+def shard_proofs(total: int, rank: int, world: int) -> List[int]:
+    """Round-robin assignment of independent proofs to ranks (BASELINE.json configs[4])."""
+    return list(range(rank, total, world))
+
+
+def g1_sum(points_raw: List[bytes]) -> bytes:
+    """Sum of affine points in the 96-byte raw layout (host-side; a few dozen additions at most)."""
+    acc = bytes(G1_RAW_BYTES)
+    out = ctypes.create_string_buffer(G1_RAW_BYTES)
+    for p in points_raw:
+        check(lib().pb200_g1_add_affine(acc, p, out))
+        acc = out.raw
+    return acc
+
+
+def allgather_g1_sum(partial_raw: bytes, device=None) -> bytes:
+    """All-gather every rank's partial MSM result and add them (same value on all ranks)."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return partial_raw
+    t = torch.frombuffer(bytearray(partial_raw), dtype=torch.uint8)
+    if device is not None:
+        t = t.to(device)
+    outs = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(outs, t)
+    return g1_sum([bytes(o.cpu().numpy().tobytes()) for o in outs])
+
+
+def max_over_ranks(ms: float, device=None) -> float:
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return ms
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sharded_msm(key, scalars: bytes, device=None) -> bytes:
+    """One MSM over the whole commit key with points partitioned across ranks.  `key` is a
+    plonk_b200.CommitKey holding the full key on every rank (bases are static and pre-placed);
+    `scalars` is the full scalar vector, each rank only touches its slice."""
+    import torch.distributed as dist
+
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    n = len(scalars) // 32
+    first, count = shard_range(n, rank, world)
+    out = ctypes.create_string_buffer(G1_RAW_BYTES)
+    sl = scalars[first * 32 : (first + count) * 32]
+    check(lib().pb200_msm_g1_range(key._h, first, sl if count else None, count, out))
+    return allgather_g1_sum(out.raw, device)

@@ -151,3 +151,15 @@ def test_msm_large_known_discrete_log(pb):
     for g, s in zip(got, polys):
         k = sum(si * (p0 + i * step) for i, si in enumerate(s)) % R.R_MOD
         assert R.g1_from_raw_bytes(g.raw) == R.g1_mul(R.G1_GEN, k)
+
+
+def test_srs_setup_matches_oracle(pb):
+    """PublicParameters::setup restated on the device (srs.rs:61-100) vs the oracle."""
+    from plonk_b200._lib import check, lib
+
+    x, gs = 0x1234567, 0x7654321
+    n = 40
+    out = ctypes.create_string_buffer(96 * n)
+    check(lib().pb200_srs_setup_from_secret(R.fr_to_mont_bytes(x), R.fr_to_mont_bytes(gs), n, out))
+    want = R.srs_from_secret(n, x, gs)
+    assert [R.g1_from_raw_bytes(out.raw[96 * i : 96 * i + 96]) for i in range(n)] == want
