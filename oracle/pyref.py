@@ -1187,7 +1187,7 @@ def minimal_circuit(comp: Composer) -> None:
     comp.assert_equal_constant(w, 7)
 
 
-def synthetic_arith_circuit(comp: Composer, n_gates: int, seed: int, n_public: int = 2) -> None:
+def synthetic_arith_circuit(comp: Composer, n_gates: int, seed: int, n_public: int = 2, widgets: int = 0) -> None:
     """a satisfied arithmetic-gate circuit with random witnesses, random
     copy constraints (witness re-use) and a few public inputs, grown until the composer holds
     exactly ``n_gates`` constraints.  Deterministic in ``seed`` (SplitMix64)."""
@@ -1203,6 +1203,8 @@ def synthetic_arith_circuit(comp: Composer, n_gates: int, seed: int, n_public: i
     def rfr() -> int:
         return (nxt() | (nxt() << 64) | (nxt() << 128) | (nxt() << 192)) % R_MOD
 
+    if widgets:  # `widgets` rows of every non-arithmetic gate family first
+        synthetic_widget_rows(comp, nxt, widgets, widgets, widgets, widgets)
     assert n_gates >= len(comp.constraints) + n_public + 1
     pool = [comp.append_witness(rfr()) for _ in range(4)]
     for _ in range(n_public):
@@ -1219,6 +1221,109 @@ def synthetic_arith_circuit(comp: Composer, n_gates: int, seed: int, n_public: i
         pool.append(c)
         if len(pool) > 64:
             pool.pop(nxt() % 32)
+
+
+# ---- JubJub (twisted Edwards -x^2 + y^2 = 1 + d x^2 y^2 over Fr), only what the ECC gate widgets need
+def fr_sqrt(a: int) -> Optional[int]:
+    """Tonelli-Shanks over Fr (2-adicity 32)."""
+    a %= R_MOD
+    if a == 0:
+        return 0
+    if pow(a, (R_MOD - 1) // 2, R_MOD) != 1:
+        return None
+    q, s = R_MOD - 1, 0
+    while q % 2 == 0:
+        q //= 2
+        s += 1
+    z = ROOT_OF_UNITY  # generator of the 2^32 subgroup = GENERATOR^q
+    m, c, t, r = s, z, pow(a, q, R_MOD), pow(a, (q + 1) // 2, R_MOD)
+    while t != 1:
+        i, t2 = 0, t
+        while t2 != 1:
+            t2 = t2 * t2 % R_MOD
+            i += 1
+        b = pow(c, 1 << (m - i - 1), R_MOD)
+        m, c = i, b * b % R_MOD
+        t, r = t * c % R_MOD, r * b % R_MOD
+    return r
+
+
+def jubjub_point_from_y(y: int) -> Optional[Tuple[int, int]]:
+    num = (y * y - 1) % R_MOD
+    den = (1 + EDWARDS_D * y * y) % R_MOD
+    x = fr_sqrt(num * fr_inv(den) % R_MOD)
+    return None if x is None else (x, y % R_MOD)
+
+
+def jubjub_add(p: Tuple[int, int], q: Tuple[int, int]) -> Tuple[int, int]:
+    x1, y1 = p
+    x2, y2 = q
+    t = EDWARDS_D * x1 * x2 % R_MOD * y1 % R_MOD * y2 % R_MOD
+    x3 = (x1 * y2 + y1 * x2) * fr_inv((1 + t) % R_MOD) % R_MOD
+    y3 = (y1 * y2 + x1 * x2) * fr_inv((1 - t) % R_MOD) % R_MOD
+    return (x3, y3)
+
+
+def synthetic_widget_rows(comp: Composer, nxt, n_range: int, n_logic: int, n_fixed: int, n_var: int) -> None:
+    """Satisfied rows for every non-arithmetic gate family, written straight from the identities
+    their widgets enforce (src/proof_system/widget/{range,logic,ecc/**}/proverkey.rs), so that
+    the quotient and linearisation code of all widgets is exercised by a provable circuit.
+    `nxt()` is the caller's deterministic 64-bit generator."""
+    link = lambda **w: comp.append_custom_gate({}, **w)  # a row with all selectors zero: constrains nothing
+    # range: d, c, b, a, d_next form a base-4 accumulator chain (range/proverkey.rs:32-57)
+    if n_range:
+        acc = nxt() % 4
+        d = comp.append_witness(acc)
+        for _ in range(n_range):
+            ws = []
+            for _ in range(3):
+                acc = (4 * acc + nxt() % 4) % R_MOD
+                ws.append(comp.append_witness(acc))
+            comp.append_custom_gate(dict(q_range=1), a=ws[2], b=ws[1], c=ws[0], d=d)
+            acc = (4 * acc + nxt() % 4) % R_MOD
+            d = comp.append_witness(acc)
+        link(d=d)
+    # logic: a, b, d accumulate base-4 digits of the operands and of AND / XOR; c holds the product of
+    # the two digits (logic/proverkey.rs:34-71)
+    if n_logic:
+        for q_c in (1, -1):  # AND then XOR (Constraint::logic / logic_xor)
+            A = B = D = 0
+            wa, wb, wd = (comp.append_witness(0) for _ in range(3))
+            for _ in range(n_logic):
+                qa, qb = nxt() % 4, nxt() % 4
+                wc = comp.append_witness(qa * qb)
+                comp.append_custom_gate(dict(q_logic=q_c, q_c=q_c), a=wa, b=wb, c=wc, d=wd)
+                A, B = 4 * A + qa, 4 * B + qb
+                D = 4 * D + ((qa & qb) if q_c == 1 else (qa ^ qb))
+                wa, wb, wd = comp.append_witness(A), comp.append_witness(B), comp.append_witness(D)
+            link(a=wa, b=wb, d=wd)
+    # JubJub points for the two ECC families
+    def point():
+        while True:
+            pt = jubjub_point_from_y(nxt() | (nxt() << 64) | (nxt() << 128) | ((nxt() >> 3) << 192))
+            if pt is not None and pt[0] != 0:
+                return pt
+    # fixed-base scalar mul rows (ecc/scalar_mul/fixed_base/proverkey.rs:39-103)
+    if n_fixed:
+        acc_pt, scalar = point(), nxt() % 1000
+        wx, wy, wd = comp.append_witness(acc_pt[0]), comp.append_witness(acc_pt[1]), comp.append_witness(scalar)
+        for _ in range(n_fixed):
+            beta = point()
+            bit = (nxt() % 3) - 1
+            alpha = (0, 1) if bit == 0 else (beta if bit == 1 else ((-beta[0]) % R_MOD, beta[1]))
+            wc = comp.append_witness(alpha[0] * alpha[1])
+            comp.append_custom_gate(dict(q_fixed_group_add=1, q_l=beta[0], q_r=beta[1], q_c=beta[0] * beta[1]), a=wx, b=wy, c=wc, d=wd)
+            acc_pt = jubjub_add(acc_pt, alpha)
+            scalar = (2 * scalar + bit) % R_MOD
+            wx, wy, wd = comp.append_witness(acc_pt[0]), comp.append_witness(acc_pt[1]), comp.append_witness(scalar)
+        link(a=wx, b=wy, d=wd)
+    # variable-base curve addition rows (ecc/curve_addition/proverkey.rs:33-79)
+    for _ in range(n_var):
+        p1, p2 = point(), point()
+        p3 = jubjub_add(p1, p2)
+        comp.append_custom_gate(dict(q_variable_group_add=1), a=comp.append_witness(p1[0]), b=comp.append_witness(p1[1]),
+                                c=comp.append_witness(p2[0]), d=comp.append_witness(p2[1]))
+        link(a=comp.append_witness(p3[0]), b=comp.append_witness(p3[1]), d=comp.append_witness(p1[0] * p2[1]))
 
 
 KAT_DIGEST = bytes.fromhex(

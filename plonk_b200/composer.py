@@ -112,7 +112,104 @@ class Composer:
                              _mont_bytes([self.public_inputs[i] for i in idx]))
 
 
-def synthetic_circuit(n_gates: int, seed: int, n_public: int = 2) -> Composer:
+EDWARDS_D = (-10240 * pow(10241, R_MOD - 2, R_MOD)) % R_MOD  # dusk_jubjub::EDWARDS_D
+_TWO_ADIC_ROOT = pow(7, (R_MOD - 1) >> 32, R_MOD)
+
+
+def _fr_sqrt(a: int):
+    """Tonelli-Shanks over Fr (2-adicity 32); None for non-residues."""
+    a %= R_MOD
+    if a == 0:
+        return 0
+    if pow(a, (R_MOD - 1) // 2, R_MOD) != 1:
+        return None
+    q, s = R_MOD - 1, 0
+    while q % 2 == 0:
+        q //= 2
+        s += 1
+    m, c, t, r = s, _TWO_ADIC_ROOT, pow(a, q, R_MOD), pow(a, (q + 1) // 2, R_MOD)
+    while t != 1:
+        i, t2 = 0, t
+        while t2 != 1:
+            t2 = t2 * t2 % R_MOD
+            i += 1
+        b = pow(c, 1 << (m - i - 1), R_MOD)
+        m, c = i, b * b % R_MOD
+        t, r = t * c % R_MOD, r * b % R_MOD
+    return r
+
+
+def _jubjub_from_y(y: int):
+    x = _fr_sqrt((y * y - 1) * pow((1 + EDWARDS_D * y * y) % R_MOD, R_MOD - 2, R_MOD) % R_MOD)
+    return None if x is None else (x, y % R_MOD)
+
+
+def _jubjub_add(p, q):
+    (x1, y1), (x2, y2) = p, q
+    t = EDWARDS_D * x1 * x2 % R_MOD * y1 % R_MOD * y2 % R_MOD
+    inv = lambda v: pow(v % R_MOD, R_MOD - 2, R_MOD)
+    return ((x1 * y2 + y1 * x2) * inv(1 + t) % R_MOD, (y1 * y2 + x1 * x2) * inv(1 - t) % R_MOD)
+
+
+def widget_rows(comp: "Composer", nxt, n_range: int, n_logic: int, n_fixed: int, n_var: int) -> None:
+    """Satisfied rows for the range, logic, fixed-base and curve-addition gate families, written from
+    the identities their widgets enforce (reference src/proof_system/widget/{range,logic,ecc/**}/
+    proverkey.rs).  The reference builds such rows with its gadget library
+    (src/composer/{range,logic,fixed_base,point}.rs); the prover backend only sees the rows."""
+    link = lambda **w: comp.append_custom_gate({}, **w)
+    if n_range:
+        acc = nxt() % 4
+        d = comp.append_witness(acc)
+        for _ in range(n_range):
+            ws = []
+            for _ in range(3):
+                acc = (4 * acc + nxt() % 4) % R_MOD
+                ws.append(comp.append_witness(acc))
+            comp.append_custom_gate(dict(q_range=1), a=ws[2], b=ws[1], c=ws[0], d=d)
+            acc = (4 * acc + nxt() % 4) % R_MOD
+            d = comp.append_witness(acc)
+        link(d=d)
+    if n_logic:
+        for q_c in (1, -1):
+            A = B = D = 0
+            wa, wb, wd = (comp.append_witness(0) for _ in range(3))
+            for _ in range(n_logic):
+                qa, qb = nxt() % 4, nxt() % 4
+                wc = comp.append_witness(qa * qb)
+                comp.append_custom_gate(dict(q_logic=q_c, q_c=q_c), a=wa, b=wb, c=wc, d=wd)
+                A, B = 4 * A + qa, 4 * B + qb
+                D = 4 * D + ((qa & qb) if q_c == 1 else (qa ^ qb))
+                wa, wb, wd = comp.append_witness(A), comp.append_witness(B), comp.append_witness(D)
+            link(a=wa, b=wb, d=wd)
+
+    def point():
+        while True:
+            pt = _jubjub_from_y(nxt() | (nxt() << 64) | (nxt() << 128) | ((nxt() >> 3) << 192))
+            if pt is not None and pt[0] != 0:
+                return pt
+
+    if n_fixed:
+        acc_pt, scalar = point(), nxt() % 1000
+        wx, wy, wd = comp.append_witness(acc_pt[0]), comp.append_witness(acc_pt[1]), comp.append_witness(scalar)
+        for _ in range(n_fixed):
+            beta = point()
+            bit = (nxt() % 3) - 1
+            alpha = (0, 1) if bit == 0 else (beta if bit == 1 else ((-beta[0]) % R_MOD, beta[1]))
+            wc = comp.append_witness(alpha[0] * alpha[1])
+            comp.append_custom_gate(dict(q_fixed_group_add=1, q_l=beta[0], q_r=beta[1], q_c=beta[0] * beta[1]), a=wx, b=wy, c=wc, d=wd)
+            acc_pt = _jubjub_add(acc_pt, alpha)
+            scalar = (2 * scalar + bit) % R_MOD
+            wx, wy, wd = comp.append_witness(acc_pt[0]), comp.append_witness(acc_pt[1]), comp.append_witness(scalar)
+        link(a=wx, b=wy, d=wd)
+    for _ in range(n_var):
+        p1, p2 = point(), point()
+        p3 = _jubjub_add(p1, p2)
+        comp.append_custom_gate(dict(q_variable_group_add=1), a=comp.append_witness(p1[0]), b=comp.append_witness(p1[1]),
+                                c=comp.append_witness(p2[0]), d=comp.append_witness(p2[1]))
+        link(a=comp.append_witness(p3[0]), b=comp.append_witness(p3[1]), d=comp.append_witness(p1[0] * p2[1]))
+
+
+def synthetic_circuit(n_gates: int, seed: int, n_public: int = 2, widgets: int = 0) -> Composer:
     """The bench workload: a satisfied arithmetic-gate circuit with random
     witnesses, random copy constraints and a few public inputs, exactly `n_gates` constraints."""
     comp = Composer.initialized()
@@ -128,6 +225,8 @@ def synthetic_circuit(n_gates: int, seed: int, n_public: int = 2) -> Composer:
     def rfr() -> int:
         return (nxt() | (nxt() << 64) | (nxt() << 128) | (nxt() << 192)) % R_MOD
 
+    if widgets:
+        widget_rows(comp, nxt, widgets, widgets, widgets, widgets)
     pool = [comp.append_witness(rfr()) for _ in range(4)]
     for _ in range(n_public):
         pool.append(comp.append_public(rfr()))

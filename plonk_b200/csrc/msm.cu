@@ -170,16 +170,22 @@ __global__ void k_msm_digits(const uint4* scalars, size_t n, size_t stride, int 
 }
 
 // Exclusive scan of counts[b][0..nb) into offsets[b][0..nb]; one CTA of 1024 threads per b.
-__global__ void __launch_bounds__(1024) k_msm_scan(const unsigned* counts, unsigned* offsets, unsigned nb) {
+// The same CTA also emits `order`: the bucket ids sorted by descending size (counting sort on the
+// clipped size), so that the threads of a warp in k_msm_accumulate get buckets of near-equal length
+// and the warp does not idle on its longest lane.
+__global__ void __launch_bounds__(1024) k_msm_scan(const unsigned* counts, unsigned* offsets, unsigned* order, unsigned nb) {
   __shared__ unsigned sums[1024];
+  __shared__ unsigned bins[1024];
   const unsigned b = blockIdx.x, tid = threadIdx.x;
   const unsigned* cnt = counts + (size_t)b * nb;
   unsigned* off = offsets + (size_t)b * (nb + 1);
+  unsigned* ord = order + (size_t)b * nb;
   const unsigned chunk = (nb + 1023) / 1024;
   const unsigned lo = tid * chunk, hi = min(nb, lo + chunk);
   unsigned s = 0;
   for (unsigned k = lo; k < hi; k++) s += cnt[k];
   sums[tid] = s;
+  bins[tid] = 0;
   __syncthreads();
   for (unsigned d = 1; d < 1024; d <<= 1) {
     unsigned v = (tid >= d) ? sums[tid - d] : 0;
@@ -193,6 +199,24 @@ __global__ void __launch_bounds__(1024) k_msm_scan(const unsigned* counts, unsig
     run += cnt[k];
   }
   if (tid == 1023) off[nb] = sums[1023];
+  // counting sort of the buckets by size, largest first (bin 0 = size >= 1023)
+  for (unsigned k = tid; k < nb; k += 1024) atomicAdd(&bins[1023u - min(cnt[k], 1023u)], 1u);
+  __syncthreads();
+  const unsigned mine = bins[tid];
+  sums[tid] = mine;
+  __syncthreads();
+  for (unsigned d = 1; d < 1024; d <<= 1) {
+    unsigned v = (tid >= d) ? sums[tid - d] : 0;
+    __syncthreads();
+    sums[tid] += v;
+    __syncthreads();
+  }
+  bins[tid] = sums[tid] - mine;  // exclusive start of each bin
+  __syncthreads();
+  for (unsigned k = tid; k < nb; k += 1024) {
+    const unsigned pos = atomicAdd(&bins[1023u - min(cnt[k], 1023u)], 1u);
+    ord[pos] = k;
+  }
 }
 
 __global__ void k_msm_scatter(const unsigned* ebkt, const unsigned* epos, const unsigned* offsets, size_t n,
@@ -208,21 +232,39 @@ __global__ void k_msm_scatter(const unsigned* ebkt, const unsigned* epos, const 
   sorted[(size_t)b * n * W + dst] = (unsigned)(((size_t)w * n_table + first + i) << 1) | sign;
 }
 
-// Bucket accumulation: thread = (bucket, part).  partial is [batch][nb][split] XYZZ.
-__global__ void __launch_bounds__(128) k_msm_accumulate(const uint4* table, const unsigned* sorted,
-                                                        const unsigned* offsets, unsigned nb, int log_split,
-                                                        size_t cap, uint4* partial) {
+PB_D G1Xyzz shfl_down_xyzz(const G1Xyzz& p, int delta, int width) {
+  G1Xyzz r;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    r.x.v[i] = __shfl_down_sync(0xffffffffu, p.x.v[i], delta, width);
+    r.y.v[i] = __shfl_down_sync(0xffffffffu, p.y.v[i], delta, width);
+    r.zz.v[i] = __shfl_down_sync(0xffffffffu, p.zz.v[i], delta, width);
+    r.zzz.v[i] = __shfl_down_sync(0xffffffffu, p.zzz.v[i], delta, width);
+  }
+  return r;
+}
+
+// Bucket accumulation: thread = (bucket, part); the 2^log_split parts of a bucket are adjacent
+// lanes and are merged with a warp-shuffle tree, so `sums` holds one XYZZ point per bucket
+// ([batch][nb]).  Buckets are visited in `order` (largest first, near-equal sizes per warp).
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(128, MIN_CTAS) k_msm_accumulate(const uint4* table, const unsigned* sorted,
+                                                               const unsigned* offsets, const unsigned* order, unsigned nb,
+                                                               int log_split, size_t cap, uint4* sums) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned split = 1u << log_split;
-  if (t >= ((size_t)nb << log_split)) return;
+  const bool valid = t < ((size_t)nb << log_split);
   const unsigned b = blockIdx.y;
-  const unsigned bucket = (unsigned)(t >> log_split), part = (unsigned)t & (split - 1);
-  const unsigned* off = offsets + (size_t)b * (nb + 1);
-  const unsigned start = off[bucket], end = off[bucket + 1];
-  const unsigned len = end - start;
-  const unsigned chunk = (len + split - 1) >> log_split;
-  unsigned lo = start + part * chunk;
-  unsigned hi = min(end, lo + chunk);
+  const unsigned part = (unsigned)t & (split - 1);
+  unsigned bucket = 0, lo = 0, hi = 0;
+  if (valid) {
+    bucket = order[(size_t)b * nb + (t >> log_split)];
+    const unsigned* off = offsets + (size_t)b * (nb + 1);
+    const unsigned start = off[bucket], end = off[bucket + 1];
+    const unsigned chunk = (end - start + split - 1) >> log_split;
+    lo = min(end, start + part * chunk);
+    hi = min(end, lo + chunk);
+  }
   const unsigned* src = sorted + (size_t)b * cap;
   G1Xyzz acc = G1Xyzz::identity();
   for (unsigned k = lo; k < hi; k++) {
@@ -232,69 +274,115 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(const uint4* table, cons
     if (e & 1u) p.y = p.y.neg();
     xyzz_madd(acc, p.x, p.y);
   }
-  st_xyzz(partial, ((size_t)b * nb + bucket) * split + part, acc);
+  for (int d = (int)split >> 1; d > 0; d >>= 1) {
+    G1Xyzz o = shfl_down_xyzz(acc, d, (int)split);
+    xyzz_add(acc, o);
+  }
+  if (valid && part == 0) st_xyzz(sums, (size_t)b * nb + bucket, acc);
 }
 
-// Running sums over groups of g consecutive buckets (also merges the SPLIT partials of a bucket):
-// S[G] = sum_j B[Gg + j],  A[G] = sum_j (j + 1) B[Gg + j].
-__global__ void __launch_bounds__(64) k_msm_groups(const uint4* partial, unsigned nb, int log_split, int g,
-                                                   uint4* S, uint4* A) {
+// ---------------------------------------------------------------------------------------------
+// Bucket reduction  R = sum_b (b + 1) B_b.  A single GPU thread needs ~15 us per dependent group
+// addition (14 carry-chained Fp products), so the reduction is organised to be work-efficient first
+// (it shares the SMs with other proofs' accumulation kernels) and shallow second:
+//   A. k_msm_groups: one thread per group of g = 8 consecutive buckets, running sums:
+//        S_G = sum_j B[8G + j],  A_G = sum_j (j + 1) B[8G + j]          => R = sum A_G + 8 sum G S_G
+//   B. k_msm_group_classes: the group index G is cut into digits of <= 4 bits; class (j, v) is the
+//      plain sum of S_G over the groups whose digit j equals v; further classes hold partial plain
+//      sums of A_G.  One warp per class: 8..16 serial additions per lane + a 5-level shuffle tree.
+//   C. k_msm_final: one warp per digit turns its 16 class sums into D_j = sum_v v C_{j,v} (suffix
+//      scan + reduce); one more warp adds the A partials.  The host finishes with a Horner over
+//      the digits (a dozen doublings, ~10 us) and the affine normalisation.
+// ---------------------------------------------------------------------------------------------
+struct DigitPlan {
+  int ndig;
+  int shift[8];
+  int bits[8];
+  int first_class[8];  // prefix sum of 2^bits
+  int n_digit_classes;
+  int n_a_classes;     // partial sums of A_G, 256 groups each
+  int nclasses;
+};
+
+__global__ void __launch_bounds__(64) k_msm_groups(const uint4* sums, unsigned nb, int g, uint4* S, uint4* A) {
   const unsigned G = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned n_groups = nb / g;
   if (G >= n_groups) return;
   const unsigned b = blockIdx.y;
-  const unsigned split = 1u << log_split;
   G1Xyzz run = G1Xyzz::identity(), acc = G1Xyzz::identity();
   for (int j = g - 1; j >= 0; j--) {
-    const size_t base = ((size_t)b * nb + (size_t)G * g + j) * split;
-    for (unsigned p = 0; p < split; p++) {
-      G1Xyzz q = ld_xyzz(partial, base + p);
-      xyzz_add(run, q);
-    }
+    G1Xyzz q = ld_xyzz(sums, (size_t)b * nb + (size_t)G * g + j);
+    xyzz_add(run, q);
     xyzz_add(acc, run);
   }
   st_xyzz(S, (size_t)b * n_groups + G, run);
   st_xyzz(A, (size_t)b * n_groups + G, acc);
 }
 
-// Class sums, 8 inputs per thread.  class k < nbits: sum of S[G] over G with bit k set;
-// class nbits: sum of A[G].  out is [batch][nbits+1][n_out].
-__global__ void __launch_bounds__(64) k_msm_class_sums(const uint4* S, const uint4* A, unsigned n, int nbits,
-                                                       unsigned n_out, uint4* out) {
-  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_out) return;
-  const int k = blockIdx.y;
-  const unsigned b = blockIdx.z;
+PB_D G1Xyzz warp_sum(G1Xyzz v) {
+  for (int d = 16; d > 0; d >>= 1) {
+    G1Xyzz o = shfl_down_xyzz(v, d, 32);
+    xyzz_add(v, o);
+  }
+  return v;
+}
+
+// One warp per class; 4 warps per CTA.  out is [batch][nclasses].
+__global__ void __launch_bounds__(128) k_msm_group_classes(const uint4* S, const uint4* A, unsigned n_groups,
+                                                           DigitPlan plan, uint4* out) {
+  const int cls = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const unsigned b = blockIdx.y;
+  if (cls >= plan.nclasses) return;
   G1Xyzz acc = G1Xyzz::identity();
-  for (unsigned u = 0; u < 8; u++) {
-    const unsigned G = t * 8 + u;
-    if (G >= n) break;
-    if (k < nbits) {
-      if ((G >> k) & 1u) {
-        G1Xyzz q = ld_xyzz(S, (size_t)b * n + G);
-        xyzz_add(acc, q);
-      }
-    } else {
-      G1Xyzz q = ld_xyzz(A, (size_t)b * n + G);
+  if (cls < plan.n_digit_classes) {
+    int j = 0;
+    while (j + 1 < plan.ndig && cls >= plan.first_class[j + 1]) j++;
+    const unsigned v = cls - plan.first_class[j];
+    const int sh_j = plan.shift[j], bits_j = plan.bits[j];
+    const unsigned count = n_groups >> bits_j;
+    for (unsigned idx = lane; idx < count; idx += 32) {
+      const unsigned G = ((idx >> sh_j) << (sh_j + bits_j)) | (v << sh_j) | (idx & ((1u << sh_j) - 1u));
+      G1Xyzz q = ld_xyzz(S, (size_t)b * n_groups + G);
+      xyzz_add(acc, q);
+    }
+  } else {
+    const unsigned first = (unsigned)(cls - plan.n_digit_classes) * 256u;
+    for (unsigned G = first + lane; G < min(n_groups, first + 256u); G += 32) {
+      G1Xyzz q = ld_xyzz(A, (size_t)b * n_groups + G);
       xyzz_add(acc, q);
     }
   }
-  st_xyzz(out, ((size_t)b * (nbits + 1) + k) * n_out + t, acc);
+  acc = warp_sum(acc);
+  if (lane == 0) st_xyzz(out, (size_t)b * plan.nclasses + cls, acc);
 }
 
-// rows x n -> rows x ceil(n/8)
-__global__ void __launch_bounds__(64) k_msm_sum8(const uint4* in, unsigned n, unsigned n_out, uint4* out) {
-  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_out) return;
-  const unsigned row = blockIdx.y;
-  G1Xyzz acc = G1Xyzz::identity();
-  for (unsigned u = 0; u < 8; u++) {
-    const unsigned i = t * 8 + u;
-    if (i >= n) break;
-    G1Xyzz q = ld_xyzz(in, (size_t)row * n + i);
-    xyzz_add(acc, q);
+// out is [batch][ndig + 1]: D_0 .. D_{ndig-1}, then the sum of all A_G.
+__global__ void __launch_bounds__(256) k_msm_final(const uint4* classes, DigitPlan plan, uint4* out) {
+  const int lane = threadIdx.x & 31, j = threadIdx.x >> 5;
+  const unsigned b = blockIdx.x;
+  if (j < plan.ndig) {
+    const int nv = 1 << plan.bits[j];
+    G1Xyzz x = (lane < nv) ? ld_xyzz(classes, (size_t)b * plan.nclasses + plan.first_class[j] + lane) : G1Xyzz::identity();
+    for (int d = 1; d < nv; d <<= 1) {  // inclusive suffix scan over lanes 0..nv-1
+      G1Xyzz o = shfl_down_xyzz(x, d, 32);
+      if (lane + d < nv) xyzz_add(x, o);
+    }
+    G1Xyzz y = (lane >= 1 && lane < nv) ? x : G1Xyzz::identity();
+    for (int d = nv >> 1; d > 0; d >>= 1) {
+      G1Xyzz o = shfl_down_xyzz(y, d, 32);
+      xyzz_add(y, o);
+    }
+    if (lane == 0) st_xyzz(out, (size_t)b * (plan.ndig + 1) + j, y);
+  } else if (j == 7) {
+    G1Xyzz acc = G1Xyzz::identity();
+    for (int k = lane; k < plan.n_a_classes; k += 32) {
+      G1Xyzz q = ld_xyzz(classes, (size_t)b * plan.nclasses + plan.n_digit_classes + k);
+      xyzz_add(acc, q);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) st_xyzz(out, (size_t)b * (plan.ndig + 1) + plan.ndig, acc);
   }
-  st_xyzz(out, (size_t)row * n_out + t, acc);
 }
 
 __global__ void k_selftest_fr_mul(const uint4* a, const uint4* b, uint4* o, size_t n) {
@@ -377,34 +465,51 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
   int log_split = 0;
   {
     const size_t avg = cap / nb;
-    while (log_split < 6 && ((size_t)nb * batch << log_split) < (1u << 18) && (avg >> (log_split + 1)) >= 8) log_split++;
+    while (log_split < 5 && ((size_t)nb * batch << log_split) < (1u << 18) && (avg >> (log_split + 1)) >= 8) log_split++;
     if (const char* env = getenv("PB200_MSM_LOG_SPLIT")) log_split = atoi(env);
   }
-  const unsigned split = 1u << log_split;
   const int g = std::min<unsigned>(kGroup, nb);
   const unsigned n_groups = nb / g;
-  int nbits = 0;
-  while ((1u << nbits) < n_groups) nbits++;
+  int log_g = 0;
+  while ((1 << log_g) < g) log_g++;
+  DigitPlan plan;
+  {
+    int total_bits = 0;
+    while ((1u << total_bits) < n_groups) total_bits++;
+    plan.ndig = (total_bits + 3) / 4;
+    int sh = 0, cls = 0;
+    for (int j = 0; j < plan.ndig; j++) {
+      const int bits = (total_bits - sh) / (plan.ndig - j);  // spread evenly, low digits first
+      plan.shift[j] = sh;
+      plan.bits[j] = bits;
+      plan.first_class[j] = cls;
+      sh += bits;
+      cls += 1 << bits;
+    }
+    plan.n_digit_classes = cls;
+    plan.n_a_classes = (int)((n_groups + 255) / 256);
+    plan.nclasses = plan.n_digit_classes + plan.n_a_classes;
+    if (plan.ndig > 7) return fail(PB200_ERR_INVALID_ARG, "window too wide for the bucket reduction");
+  }
 
-  unsigned *counts = nullptr, *offsets = nullptr, *ebkt = nullptr, *epos = nullptr, *sorted = nullptr;
-  uint4 *partial = nullptr, *S = nullptr, *A = nullptr, *t0 = nullptr, *t1 = nullptr;
+  unsigned *counts = nullptr, *offsets = nullptr, *order = nullptr, *ebkt = nullptr, *epos = nullptr, *sorted = nullptr;
+  uint4 *sums = nullptr, *classes = nullptr, *S = nullptr, *A = nullptr, *result = nullptr;
   PB_CUDA(cudaMallocAsync((void**)&counts, (size_t)batch * nb * 4, st));
   PB_CUDA(cudaMallocAsync((void**)&offsets, (size_t)batch * (nb + 1) * 4, st));
+  PB_CUDA(cudaMallocAsync((void**)&order, (size_t)batch * nb * 4, st));
   PB_CUDA(cudaMallocAsync((void**)&ebkt, (size_t)batch * cap * 4, st));
   PB_CUDA(cudaMallocAsync((void**)&epos, (size_t)batch * cap * 4, st));
   PB_CUDA(cudaMallocAsync((void**)&sorted, (size_t)batch * cap * 4, st));
-  PB_CUDA(cudaMallocAsync((void**)&partial, (size_t)batch * nb * split * 192, st));
+  PB_CUDA(cudaMallocAsync((void**)&sums, (size_t)batch * nb * 192, st));
+  PB_CUDA(cudaMallocAsync((void**)&classes, (size_t)batch * plan.nclasses * 192, st));
   PB_CUDA(cudaMallocAsync((void**)&S, (size_t)batch * n_groups * 192, st));
   PB_CUDA(cudaMallocAsync((void**)&A, (size_t)batch * n_groups * 192, st));
-  const unsigned rows = batch * (nbits + 1);
-  const unsigned n1 = (n_groups + 7) / 8;
-  PB_CUDA(cudaMallocAsync((void**)&t0, (size_t)rows * n1 * 192, st));
-  PB_CUDA(cudaMallocAsync((void**)&t1, (size_t)rows * ((n1 + 7) / 8) * 192, st));
+  PB_CUDA(cudaMallocAsync((void**)&result, (size_t)batch * (plan.ndig + 1) * 192, st));
   PB_CUDA(cudaMemsetAsync(counts, 0, (size_t)batch * nb * 4, st));
 
   PB_LAUNCH(k_msm_digits, dim3(div_up(n, 128), batch), 128, 0, st, (const uint4*)d_scalars, n, stride, c, W, nb,
             counts, ebkt, epos);
-  PB_LAUNCH(k_msm_scan, batch, 1024, 0, st, counts, offsets, nb);
+  PB_LAUNCH(k_msm_scan, batch, 1024, 0, st, counts, offsets, order, nb);
   PB_LAUNCH(k_msm_scatter, dim3(div_up(n, 256), W, batch), 256, 0, st, ebkt, epos, offsets, n, W, nb,
             srs->n_points, first, sorted);
   const bool prof = g_prof_on.load(std::memory_order_relaxed) != 0;
@@ -414,26 +519,31 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
     PB_CUDA(cudaEventCreate(&ev1));
     PB_CUDA(cudaEventRecord(ev0, st));
   }
-  PB_LAUNCH(k_msm_accumulate, dim3(div_up((size_t)nb << log_split, 128), batch), 128, 0, st, srs->table, sorted,
-            offsets, nb, log_split, cap, partial);
+  {
+    static const int min_ctas = [] {
+      const char* e = getenv("PB200_ACC_MIN_CTAS");
+      return e ? atoi(e) : 2;
+    }();
+    const dim3 grid(div_up((size_t)nb << log_split, 128), batch);
+    if (min_ctas >= 4)
+      PB_LAUNCH(k_msm_accumulate<4>, grid, 128, 0, st, srs->table, sorted, offsets, order, nb, log_split, cap, sums);
+    else if (min_ctas == 3)
+      PB_LAUNCH(k_msm_accumulate<3>, grid, 128, 0, st, srs->table, sorted, offsets, order, nb, log_split, cap, sums);
+    else
+      PB_LAUNCH(k_msm_accumulate<2>, grid, 128, 0, st, srs->table, sorted, offsets, order, nb, log_split, cap, sums);
+  }
   std::vector<unsigned> h_tot(batch, 0);
   if (prof) {
     PB_CUDA(cudaEventRecord(ev1, st));
     PB_CUDA(cudaMemcpy2DAsync(h_tot.data(), 4, offsets + nb, (size_t)(nb + 1) * 4, 4, batch, cudaMemcpyDeviceToHost, st));
   }
-  PB_LAUNCH(k_msm_groups, dim3(div_up(n_groups, 64), batch), 64, 0, st, partial, nb, log_split, g, S, A);
-  PB_LAUNCH(k_msm_class_sums, dim3(div_up(n1, 64), nbits + 1, batch), 64, 0, st, S, A, n_groups, nbits, n1, t0);
-  unsigned cur = n1;
-  uint4 *src = t0, *dst = t1;
-  while (cur > 1) {
-    const unsigned nxt = (cur + 7) / 8;
-    PB_LAUNCH(k_msm_sum8, dim3(div_up(nxt, 64), rows), 64, 0, st, src, cur, nxt, dst);
-    std::swap(src, dst);
-    cur = nxt;
-  }
+  PB_LAUNCH(k_msm_groups, dim3(div_up(n_groups, 64), batch), 64, 0, st, (const uint4*)sums, nb, g, S, A);
+  PB_LAUNCH(k_msm_group_classes, dim3(div_up(plan.nclasses, 4), batch), 128, 0, st, (const uint4*)S, (const uint4*)A, n_groups,
+            plan, classes);
+  PB_LAUNCH(k_msm_final, batch, 256, 0, st, (const uint4*)classes, plan, result);
   PB_CUDA(cudaGetLastError());
-  std::vector<uint32_t> host((size_t)rows * cur * 48);
-  PB_CUDA(cudaMemcpyAsync(host.data(), src, host.size() * 4, cudaMemcpyDeviceToHost, st));
+  std::vector<uint32_t> host((size_t)batch * (plan.ndig + 1) * 48);
+  PB_CUDA(cudaMemcpyAsync(host.data(), result, host.size() * 4, cudaMemcpyDeviceToHost, st));
   PB_CUDA(cudaStreamSynchronize(st));
   if (prof) {
     float ms = 0;
@@ -448,31 +558,23 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
   }
-  cudaFreeAsync(counts, st); cudaFreeAsync(offsets, st); cudaFreeAsync(ebkt, st); cudaFreeAsync(epos, st);
-  cudaFreeAsync(sorted, st); cudaFreeAsync(partial, st); cudaFreeAsync(S, st); cudaFreeAsync(A, st);
-  cudaFreeAsync(t0, st); cudaFreeAsync(t1, st);
+  cudaFreeAsync(counts, st); cudaFreeAsync(offsets, st); cudaFreeAsync(order, st); cudaFreeAsync(ebkt, st);
+  cudaFreeAsync(epos, st); cudaFreeAsync(sorted, st); cudaFreeAsync(sums, st); cudaFreeAsync(classes, st);
+  cudaFreeAsync(S, st); cudaFreeAsync(A, st); cudaFreeAsync(result, st);
 
-  // Host tail: result = U + g * sum_k 2^k C_k  (U = sum of A[G], C_k = sum of S[G] over bit k of G).
-  int log_g = 0;
-  while ((1 << log_g) < g) log_g++;
+  // Host tail: R = sum A_G + g * sum_j 2^shift_j D_j (Horner over the digits), then one inversion per
+  // result (Commitment::from, commitment.rs:89-93).
   for (uint32_t b = 0; b < batch; b++) {
-    std::vector<pbh::HXyzz> cls(nbits + 1);
-    for (int k = 0; k <= nbits; k++) {
-      pbh::HXyzz acc = pbh::HXyzz::identity();
-      for (unsigned u = 0; u < cur; u++) {
-        pbh::HXyzz q;
-        xyzz_dev_to_host(host.data() + (((size_t)b * (nbits + 1) + k) * cur + u) * 48, &q);
-        pbh::hxyzz_add(acc, q);
-      }
-      cls[k] = acc;
+    const uint32_t* hp = host.data() + (size_t)b * (plan.ndig + 1) * 48;
+    pbh::HXyzz h = pbh::HXyzz::identity(), t;
+    for (int d = plan.ndig - 1; d >= 0; d--) {
+      xyzz_dev_to_host(hp + (size_t)d * 48, &t);
+      pbh::hxyzz_add(h, t);
+      const int dbl = d > 0 ? plan.bits[d - 1] : log_g;
+      for (int k = 0; k < dbl; k++) h = pbh::hxyzz_dbl(h);
     }
-    pbh::HXyzz h = pbh::HXyzz::identity();
-    for (int k = nbits - 1; k >= 0; k--) {
-      h = pbh::hxyzz_dbl(h);
-      pbh::hxyzz_add(h, cls[k]);
-    }
-    for (int k = 0; k < log_g; k++) h = pbh::hxyzz_dbl(h);
-    pbh::hxyzz_add(h, cls[nbits]);
+    xyzz_dev_to_host(hp + (size_t)plan.ndig * 48, &t);
+    pbh::hxyzz_add(h, t);
     pbh::HFp x, y;
     pbh::hxyzz_to_affine(h, &x, &y);
     memcpy(out_affine_host + (size_t)b * 12, x.v, 48);

@@ -375,7 +375,16 @@ int ntt_run(const uint64_t* d_in, size_t in_len, uint64_t* d_out, uint32_t log_n
     a.first = (q == 0);
     a.last = (q == n_pass - 1);
     a.log_r0 = (n_pass > 1) ? radices[0] : 0;
-    const int room = kMaxLogTile - a.r;
+    // tile width: as wide as shared memory allows, but narrow enough that the launch has a few
+    // CTAs per SM (small transforms are otherwise a handful of CTAs on a 148-SM part)
+    int room = kMaxLogTile - a.r;
+    {
+      int want = 0;  // log2(n * batch / target_ctas) - r
+      const size_t per_cta = ((size_t)n * batch) / 592;
+      while (((size_t)2 << (want + a.r)) <= per_cta) want++;
+      if (want < 1) want = 1;
+      if (want < room) room = want;
+    }
     a.log_t = a.last ? (a.log_r0 < room ? a.log_r0 : room) : (log_lo < room ? log_lo : room);
     a.in = (const uint4*)(a.first ? d_in : d_tmp);
     a.out = (uint4*)(a.last ? d_out : d_tmp);

@@ -655,8 +655,8 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
   unsigned* flag;
   const unsigned eval_blocks = div_up(stride, 2048);
   PB_CUDA(cudaMallocAsync((void**)&wv, 4 * n * 32, st));
-  PB_CUDA(cudaMallocAsync((void**)&wp, 4 * stride * 32, st));
-  PB_CUDA(cudaMallocAsync((void**)&zp, stride * 32, st));
+  PB_CUDA(cudaMallocAsync((void**)&zp, 5 * stride * 32, st));  // [z, a, b, c, d], one coset-NTT batch in round 3
+  wp = zp + 2 * stride;
   PB_CUDA(cudaMallocAsync((void**)&num, n * 32, st));
   PB_CUDA(cudaMallocAsync((void**)&den, n * 32, st));
   PB_CUDA(cudaMallocAsync((void**)&w8, 6 * n8 * 32, st));
@@ -671,7 +671,7 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
   PB_CUDA(cudaMallocAsync((void**)&partial, (size_t)16 * eval_blocks * 32, st));
   PB_CUDA(cudaMallocAsync((void**)&flag, 4, st));
   auto free_all = [&]() {
-    uint4* bufs[] = {wv, wp, zp, num, den, w8, quot, tcoef, tq, pi_dense, agg, pw, scratch, evals_d, partial};
+    uint4* bufs[] = {wv, zp, num, den, w8, quot, tcoef, tq, pi_dense, agg, pw, scratch, evals_d, partial};
     for (uint4* b : bufs) cudaFreeAsync(b, st);
     cudaFreeAsync(flag, st);
   };
@@ -734,9 +734,11 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
     PB_CUDA(cudaMemcpyAsync(pi_dense + 2 * pi_idx[i], PIV + i, 32, cudaMemcpyHostToDevice, st));
   if (n_pi) PB_TRY(ntt_run((const uint64_t*)pi_dense, n, (uint64_t*)(pi_dense + 2 * n), log_n, 1, 0, 1, n, n, st));
   // coset evaluations: z, a, b, c, d, pi (quotient_poly.rs:50-59, 177)
-  PB_TRY(ntt_run((const uint64_t*)zp, n + 3, (uint64_t*)w8, log_n + 3, 0, 1, 1, stride, n8, st));
-  PB_TRY(ntt_run((const uint64_t*)wp, n + 2, (uint64_t*)(w8 + 2 * n8), log_n + 3, 0, 1, 4, stride, n8, st));
-  PB_TRY(ntt_run((const uint64_t*)(pi_dense + 2 * n), n_pi ? n : 0, (uint64_t*)(w8 + 2 * 5 * n8), log_n + 3, 0, 1, 1, n, n8, st));
+  PB_TRY(ntt_run((const uint64_t*)zp, n + 3, (uint64_t*)w8, log_n + 3, 0, 1, 5, stride, n8, st));
+  if (n_pi)
+    PB_TRY(ntt_run((const uint64_t*)(pi_dense + 2 * n), n, (uint64_t*)(w8 + 2 * 5 * n8), log_n + 3, 0, 1, 1, n, n8, st));
+  else
+    PB_CUDA(cudaMemsetAsync(w8 + 2 * 5 * n8, 0, n8 * 32, st));  // empty PI polynomial: 8n zeros
   {
     QuotArgs q;
     q.w8 = w8; q.key8 = P->d_key8; q.linear8 = P->d_linear8; q.l1_8 = P->d_l1_8; q.out = quot; q.n8 = n8;

@@ -60,3 +60,18 @@ def test_cref_prover_matches_pyref_on_synthetic_circuit():
     want = R.prove(R.compile_circuit(pp, label, comp), R.StdRng.seed_from_u64(123), comp)
     got = cref.CrefProver(label, arrays, srs_raw).prove(cref.draw_blinders(R.StdRng.seed_from_u64(123)))
     assert got == want
+
+
+def test_cref_prover_all_gate_families_matches_pyref():
+    """Range, logic, fixed-base and curve-addition widgets with non-zero selectors."""
+    rng = random.Random(9)
+    srs_raw = cref.srs_from_secret(256 + 7, rng.randrange(1, R.R_MOD), rng.randrange(1, R.R_MOD))
+    pp = [R.g1_from_raw_bytes(srs_raw[96 * i : 96 * i + 96]) for i in range(263)]
+    comp = R.Composer.initialized()
+    R.synthetic_arith_circuit(comp, 150, seed=21, n_public=2, widgets=7)
+    arrays = cref.CircuitArrays(comp)
+    pd = R.compile_circuit(pp, b"widgets", comp)
+    assert all(pd.comms[k] is not None for k in R.SELECTORS)  # every selector polynomial is non-zero
+    want = R.prove(pd, R.StdRng.seed_from_u64(4), comp)
+    got = cref.CrefProver(b"widgets", arrays, srs_raw).prove(cref.draw_blinders(R.StdRng.seed_from_u64(4)))
+    assert got == want

@@ -61,6 +61,28 @@ def test_gpu_prover_matches_cpu_oracle(pb, log_gates, n_public):
         gpu.prove(bytes(bad), arrays.pi_idx, arrays.pi_vals, cref.draw_blinders(R.StdRng.seed_from_u64(3)))
 
 
+@pytest.mark.parametrize("log_gates,widgets", [(8, 6), (11, 40)])
+def test_gpu_prover_all_gate_families(pb, log_gates, widgets):
+    """Circuits with satisfied range / logic / fixed-base / curve-addition rows: every widget of the
+    quotient kernel and of the linearisation runs with a non-zero selector polynomial."""
+    rng = random.Random(100 + log_gates)
+    n_gates = (1 << log_gates) - 6
+    srs_raw = cref.srs_from_secret((1 << log_gates) + 7, rng.randrange(1, R.R_MOD), rng.randrange(1, R.R_MOD))
+    comp = R.Composer.initialized()
+    R.synthetic_arith_circuit(comp, n_gates, seed=500 + log_gates, n_public=2, widgets=widgets)
+    arrays = cref.CircuitArrays(comp)
+    cpu = cref.CrefProver(b"widgets", arrays, srs_raw)
+    gpu = _gpu_prover(pb, b"widgets", arrays, srs_raw)
+    assert gpu.commitments() == cpu.commitments()
+    assert all(c[0] & 0x40 == 0 for c in gpu.commitments()[:11])  # no selector commits to the identity
+    blinders = cref.draw_blinders(R.StdRng.seed_from_u64(77))
+    assert gpu.prove(arrays.witnesses, arrays.pi_idx, arrays.pi_vals, blinders) == cpu.prove(blinders)
+    bad = bytearray(arrays.witnesses)
+    bad[32 * 10] ^= 1  # breaks a range row
+    with pytest.raises(pb.CircuitUnsatisfied):
+        gpu.prove(bytes(bad), arrays.pi_idx, arrays.pi_vals, blinders)
+
+
 def test_gpu_prover_2_16_gates_matches_cpu_oracle(pb):
     """BASELINE.json configs[1]: 2^16-gate circuit, Proof bytes == CPU restatement."""
     n_gates = (1 << 16) - 6

@@ -15,6 +15,13 @@ def test_product_composer_matches_oracle_composer():
     ref = cref.CircuitArrays(comp)
     for f in ("constraints", "selectors", "wires", "witnesses", "pi_idx", "pi_vals", "n_witnesses", "n_pi"):
         assert getattr(ours, f) == getattr(ref, f), f
+    # with rows of every gate family
+    ours = synthetic_circuit(200, seed=9, n_public=1, widgets=6).arrays()
+    comp = R.Composer.initialized()
+    R.synthetic_arith_circuit(comp, 200, seed=9, n_public=1, widgets=6)
+    ref = cref.CircuitArrays(comp)
+    for f in ("constraints", "selectors", "wires", "witnesses", "pi_idx", "pi_vals"):
+        assert getattr(ours, f) == getattr(ref, f), f
 
 
 def test_library_exports_every_declared_symbol():

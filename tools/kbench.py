@@ -73,6 +73,12 @@ try:
             out = ctypes.create_string_buffer(96 * batch)
             f = lambda: check(L.pb200_msm_g1_dev(h, s.data_ptr(), n, batch, n, out, stream))
             ms = time_ms(f, iters=5, warm=2)
+            L.pb200_profile_enable(1)
+            f(); f()
+            acc_ms, adds, nl, pts = ctypes.c_double(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+            L.pb200_profile_read(ctypes.byref(acc_ms), ctypes.byref(adds), ctypes.byref(nl), ctypes.byref(pts))
+            L.pb200_profile_enable(0)
+            print(f"   accumulate kernel: {acc_ms.value/2:.3f} ms/launch, {adds.value/acc_ms.value/1e6:.3f} G adds/s", flush=True)
             res[f"msm_2^{log_n}_b{batch}"] = dict(ms=ms, mpoints_per_s=n * batch / ms / 1e3)
             print(f"msm 2^{log_n} batch {batch}: {ms:.3f} ms  ({n*batch/ms/1e3:.2f} M points/s)", flush=True)
         L.pb200_srs_free(h)
