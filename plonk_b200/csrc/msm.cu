@@ -267,9 +267,21 @@ __global__ void __launch_bounds__(128, MIN_CTAS) k_msm_accumulate(const uint4* t
   }
   const unsigned* src = sorted + (size_t)b * cap;
   G1Xyzz acc = G1Xyzz::identity();
+  // software pipeline: the (random, 96-byte) load of the next point is in flight during the ~3000
+  // integer instructions of the current addition
+  unsigned e_next = 0;
+  G1Affine p_next;
+  if (lo < hi) {
+    e_next = __ldg(src + lo);
+    p_next = ld_affine(table, e_next >> 1);
+  }
   for (unsigned k = lo; k < hi; k++) {
-    const unsigned e = __ldg(src + k);
-    G1Affine p = ld_affine(table, e >> 1);
+    const unsigned e = e_next;
+    G1Affine p = p_next;
+    if (k + 1 < hi) {
+      e_next = __ldg(src + k + 1);
+      p_next = ld_affine(table, e_next >> 1);
+    }
     if (p.is_inf()) continue;
     if (e & 1u) p.y = p.y.neg();
     xyzz_madd(acc, p.x, p.y);
@@ -465,7 +477,7 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
   int log_split = 0;
   {
     const size_t avg = cap / nb;
-    while (log_split < 5 && ((size_t)nb * batch << log_split) < (1u << 18) && (avg >> (log_split + 1)) >= 8) log_split++;
+    while (log_split < 5 && ((size_t)nb * batch << log_split) < (1u << 17) && (avg >> (log_split + 1)) >= 8) log_split++;
     if (const char* env = getenv("PB200_MSM_LOG_SPLIT")) log_split = atoi(env);
   }
   const int g = std::min<unsigned>(kGroup, nb);
@@ -562,8 +574,10 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
   cudaFreeAsync(epos, st); cudaFreeAsync(sorted, st); cudaFreeAsync(sums, st); cudaFreeAsync(classes, st);
   cudaFreeAsync(S, st); cudaFreeAsync(A, st); cudaFreeAsync(result, st);
 
-  // Host tail: R = sum A_G + g * sum_j 2^shift_j D_j (Horner over the digits), then one inversion per
-  // result (Commitment::from, commitment.rs:89-93).
+  // Host tail: R = sum A_G + g * sum_j 2^shift_j D_j (Horner over the digits), then the affine
+  // normalisation of Commitment::from (commitment.rs:89-93) with one shared inversion per batch
+  // (Montgomery's trick over the ZZ*ZZZ of the batch's results).
+  std::vector<pbh::HXyzz> res(batch);
   for (uint32_t b = 0; b < batch; b++) {
     const uint32_t* hp = host.data() + (size_t)b * (plan.ndig + 1) * 48;
     pbh::HXyzz h = pbh::HXyzz::identity(), t;
@@ -575,10 +589,28 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
     }
     xyzz_dev_to_host(hp + (size_t)plan.ndig * 48, &t);
     pbh::hxyzz_add(h, t);
-    pbh::HFp x, y;
-    pbh::hxyzz_to_affine(h, &x, &y);
-    memcpy(out_affine_host + (size_t)b * 12, x.v, 48);
-    memcpy(out_affine_host + (size_t)b * 12 + 6, y.v, 48);
+    res[b] = h;
+  }
+  {
+    std::vector<pbh::HFp> den(batch), pre(batch);
+    pbh::HFp acc = pbh::HFp::one();
+    for (uint32_t b = 0; b < batch; b++) {
+      den[b] = res[b].is_inf() ? pbh::HFp::one() : res[b].zz * res[b].zzz;
+      pre[b] = acc;
+      acc = acc * den[b];
+    }
+    pbh::HFp inv = acc.inv();
+    for (uint32_t b = batch; b-- > 0;) {
+      const pbh::HFp i = inv * pre[b];  // 1 / (zz * zzz)
+      inv = inv * den[b];
+      pbh::HFp x = pbh::HFp::zero(), y = pbh::HFp::zero();
+      if (!res[b].is_inf()) {
+        x = res[b].x * (i * res[b].zzz);
+        y = res[b].y * (i * res[b].zz);
+      }
+      memcpy(out_affine_host + (size_t)b * 12, x.v, 48);
+      memcpy(out_affine_host + (size_t)b * 12 + 6, y.v, 48);
+    }
   }
   return 0;
 }

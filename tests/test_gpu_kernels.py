@@ -163,3 +163,29 @@ def test_srs_setup_matches_oracle(pb):
     check(lib().pb200_srs_setup_from_secret(R.fr_to_mont_bytes(x), R.fr_to_mont_bytes(gs), n, out))
     want = R.srs_from_secret(n, x, gs)
     assert [R.g1_from_raw_bytes(out.raw[96 * i : 96 * i + 96]) for i in range(n)] == want
+
+
+def test_msm_2_20_points_against_known_secret(pb):
+    """BASELINE.json configs[2]/[3] size: 2^20-point commit key generated on the device as [x^i] g;
+    the commitment must equal [p(x)] g (SURVEY.md Appendix D note) - one scalar multiplication."""
+    from plonk_b200._lib import check, lib
+
+    rng = random.Random(20)
+    n = (1 << 20) + 7
+    x, gs = rng.randrange(1, R.R_MOD), rng.randrange(1, R.R_MOD)
+    raw = ctypes.create_string_buffer(96 * n)
+    check(lib().pb200_srs_setup_from_secret(R.fr_to_mont_bytes(x), R.fr_to_mont_bytes(gs), n, raw))
+    key = pb.CommitKey(raw.raw)
+    poly = rand_fr(rng, n - 3)
+    got = key.commit(to_abi(poly))
+    assert R.g1_from_raw_bytes(got.raw) == R.g1_mul(R.g1_mul(R.G1_GEN, gs), R.poly_eval(poly, x))
+    # partial MSMs over point ranges add up to the full one (the multi-GPU sharding of section 8e-ii)
+    from plonk_b200 import dist as pd
+
+    parts = []
+    for r in range(3):
+        first, count = pd.shard_range(len(poly), r, 3)
+        out = ctypes.create_string_buffer(96)
+        check(lib().pb200_msm_g1_range(key._h, first, to_abi(poly[first : first + count]), count, out))
+        parts.append(out.raw)
+    assert pd.g1_sum(parts) == got.raw

@@ -95,3 +95,23 @@ def test_gpu_prover_2_16_gates_matches_cpu_oracle(pb):
     assert gpu.commitments() == cpu.commitments()
     blinders = cref.draw_blinders(R.StdRng.seed_from_u64(16))
     assert gpu.prove(arrays.witnesses, arrays.pi_idx, arrays.pi_vals, blinders) == cpu.prove(blinders)
+
+
+def test_gpu_prover_2_18_gates_matches_cpu_oracle(pb):
+    """A larger domain (n = 2^18, quotient domain 2^21: three-pass NTT plan, bigger MSM tables)."""
+    log_gates = 18
+    n_gates = (1 << log_gates) - 6
+    from plonk_b200._lib import check, lib
+    import ctypes
+
+    n_srs = (1 << log_gates) + 7
+    raw = ctypes.create_string_buffer(96 * n_srs)
+    check(lib().pb200_srs_setup_from_secret(R.fr_to_mont_bytes(0xABCDEF), R.fr_to_mont_bytes(0x13579), n_srs, raw))
+    comp = R.Composer.initialized()
+    R.synthetic_arith_circuit(comp, n_gates, seed=18, widgets=3)
+    arrays = cref.CircuitArrays(comp)
+    cpu = cref.CrefProver(b"bench-2^18", arrays, raw.raw)
+    gpu = _gpu_prover(pb, b"bench-2^18", arrays, raw.raw)
+    assert gpu.commitments() == cpu.commitments()
+    blinders = cref.draw_blinders(R.StdRng.seed_from_u64(18))
+    assert gpu.prove(arrays.witnesses, arrays.pi_idx, arrays.pi_vals, blinders) == cpu.prove(blinders)
