@@ -82,6 +82,14 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def finish_dist(world):
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def build_workload():
     from plonk_b200.composer import synthetic_circuit
 
@@ -179,6 +187,7 @@ def run_ours(args):
     value = total_proofs / (ms_res * 1e-3)
     e2e_value = total_proofs / (ms_e2e * 1e-3)
     if rank != 0:
+        finish_dist(world)
         return
     # dominant kernel: MSM bucket accumulation
     hbm_peak, peak_src = measured_peaks()
@@ -219,6 +228,7 @@ def run_ours(args):
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
+    finish_dist(world)
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_msm_accumulate launch (batch 4, 2^16 points) from the

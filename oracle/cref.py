@@ -35,7 +35,17 @@ def lib():
 
 
 def threads() -> int:
-    return lib().cref_threads()
+    """Host threads for the CPU baseline: every core this process may run on.  (Not
+    omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its children, which would silently
+    make the reference arm single-threaded; every parallel region in cref.cpp takes an explicit
+    num_threads.)"""
+    env = os.environ.get("PB200_CPU_THREADS")
+    if env:
+        return int(env)
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def ntt(data: bytes, log_n: int, inverse: int, coset: int, nthreads: Optional[int] = None) -> bytes:
