@@ -18,6 +18,9 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
+        # libgomp reads OMP_NUM_THREADS when it initialises; torchrun exports OMP_NUM_THREADS=1, under
+        # which even explicit num_threads() clauses were measured to run slower than one thread.
+        os.environ["OMP_NUM_THREADS"] = str(threads())
         if not os.path.exists(_SO):
             subprocess.check_call(["make", "-C", _HERE])
         L = ctypes.CDLL(_SO)
