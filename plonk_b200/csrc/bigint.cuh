@@ -22,6 +22,10 @@
 #define PB_D inline
 #endif
 
+#ifndef PB_SPLIT
+#define PB_SPLIT 0
+#endif
+
 namespace pb {
 
 #if defined(__CUDA_ARCH__)
@@ -70,6 +74,23 @@ PB_D void mad_pair(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, uint32_t 
 PB_D void mul_pair(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
   asm volatile("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
 }
+// Same contract as mad_pair, but the 64-bit product is formed by a carry-free IMAD.WIDE and added
+// with two carry-chained IADD3 on the ALU pipe.  IMAD.WIDE.U32.X (carry in/out) issues at half the
+// rate of the carry-free form (tools/mulbench), so moving part of the links of a chain to this
+// shape balances the multiply pipe against the otherwise idle ALU pipe.
+template <bool CIN, bool COUT>
+PB_D void mad_pair_split(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, uint32_t clo, uint32_t chi) {
+  uint32_t tl, th;
+  asm volatile("{ .reg .u64 t; mul.wide.u32 t, %2, %3; mov.b64 {%0, %1}, t; }" : "=r"(tl), "=r"(th) : "r"(a), "r"(b));
+  if (CIN && COUT)
+    asm volatile("addc.cc.u32 %0, %2, %3; addc.cc.u32 %1, %4, %5;" : "=r"(lo), "=r"(hi) : "r"(clo), "r"(tl), "r"(chi), "r"(th));
+  else if (CIN && !COUT)
+    asm volatile("addc.cc.u32 %0, %2, %3; addc.u32 %1, %4, %5;" : "=r"(lo), "=r"(hi) : "r"(clo), "r"(tl), "r"(chi), "r"(th));
+  else if (!CIN && COUT)
+    asm volatile("add.cc.u32 %0, %2, %3; addc.cc.u32 %1, %4, %5;" : "=r"(lo), "=r"(hi) : "r"(clo), "r"(tl), "r"(chi), "r"(th));
+  else
+    asm volatile("add.cc.u32 %0, %2, %3; addc.u32 %1, %4, %5;" : "=r"(lo), "=r"(hi) : "r"(clo), "r"(tl), "r"(chi), "r"(th));
+}
 #else
 // Host emulation of the PTX condition-code register (one flag, as in PTX).
 static thread_local uint32_t pb_cf = 0;
@@ -95,6 +116,10 @@ inline void mad_pair(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, uint32_
   hi = h;
 }
 inline void mul_pair(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) { lo = mul_lo(a, b); hi = mul_hi(a, b); }
+template <bool CIN, bool COUT>
+inline void mad_pair_split(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, uint32_t clo, uint32_t chi) {
+  mad_pair<CIN, COUT>(lo, hi, a, b, clo, chi);
+}
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -185,36 +210,44 @@ struct Field {
   // chains of mad.lo.cc/madc.hi.cc (IMAD.WIDE.U32 with predicate carry in SASS).  After the
   // Montgomery step E[0] == 0 and T/2^32 = O + (E >> 32): the accumulators swap roles (new E = O,
   // new O = E >> 64) and the one left-over limb E[1] is folded into the next row's carry chain.
+  template <bool SPLIT, bool CIN, bool COUT>
+  static PB_HD void link(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, uint32_t clo, uint32_t chi) {
+    if (SPLIT)
+      mad_pair_split<CIN, COUT>(lo, hi, a, b, clo, chi);
+    else
+      mad_pair<CIN, COUT>(lo, hi, a, b, clo, chi);
+  }
   template <bool FIRST>
   static PB_HD void mont_row(uint32_t* X /* old E -> new O */, uint32_t* Y /* old O -> new E */,
                              const uint32_t* a, uint32_t bi) {
+    constexpr bool S0 = (PB_SPLIT & 1) != 0, S1 = (PB_SPLIT & 2) != 0, S2 = (PB_SPLIT & 4) != 0, S3 = (PB_SPLIT & 8) != 0;
     if (!FIRST) {
       Y[0] = add_cc(Y[0], X[1]);
 #pragma unroll
       for (int k = 0; k < N; k += 2) {
         if (k + 2 < N)
-          mad_pair<true, true>(X[k], X[k + 1], a[k + 1], bi, X[k + 2], X[k + 3]);
+          link<S0, true, true>(X[k], X[k + 1], a[k + 1], bi, X[k + 2], X[k + 3]);
         else
-          mad_pair<true, false>(X[k], X[k + 1], a[k + 1], bi, 0u, 0u);
+          link<S0, true, false>(X[k], X[k + 1], a[k + 1], bi, 0u, 0u);
       }
-      mad_pair<false, true>(Y[0], Y[1], a[0], bi, Y[0], Y[1]);
+      link<S1, false, true>(Y[0], Y[1], a[0], bi, Y[0], Y[1]);
 #pragma unroll
-      for (int j = 2; j < N; j += 2) mad_pair<true, true>(Y[j], Y[j + 1], a[j], bi, Y[j], Y[j + 1]);
+      for (int j = 2; j < N; j += 2) link<S1, true, true>(Y[j], Y[j + 1], a[j], bi, Y[j], Y[j + 1]);
       X[N - 1] = addc(X[N - 1], 0u);
     }
     const uint32_t m = mul_lo(Y[0], P::inv());
 #pragma unroll
     for (int k = 0; k < N; k += 2) {
       if (k == 0)
-        mad_pair<false, true>(X[k], X[k + 1], P::MOD(k + 1), m, X[k], X[k + 1]);
+        link<S2, false, true>(X[k], X[k + 1], P::MOD(k + 1), m, X[k], X[k + 1]);
       else if (k + 2 < N)
-        mad_pair<true, true>(X[k], X[k + 1], P::MOD(k + 1), m, X[k], X[k + 1]);
+        link<S2, true, true>(X[k], X[k + 1], P::MOD(k + 1), m, X[k], X[k + 1]);
       else
-        mad_pair<true, false>(X[k], X[k + 1], P::MOD(k + 1), m, X[k], X[k + 1]);
+        link<S2, true, false>(X[k], X[k + 1], P::MOD(k + 1), m, X[k], X[k + 1]);
     }
-    mad_pair<false, true>(Y[0], Y[1], P::MOD(0), m, Y[0], Y[1]);
+    link<S3, false, true>(Y[0], Y[1], P::MOD(0), m, Y[0], Y[1]);
 #pragma unroll
-    for (int j = 2; j < N; j += 2) mad_pair<true, true>(Y[j], Y[j + 1], P::MOD(j), m, Y[j], Y[j + 1]);
+    for (int j = 2; j < N; j += 2) link<S3, true, true>(Y[j], Y[j + 1], P::MOD(j), m, Y[j], Y[j + 1]);
     X[N - 1] = addc(X[N - 1], 0u);
   }
 

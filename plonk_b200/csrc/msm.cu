@@ -37,7 +37,8 @@ struct pb200_srs {
 
 namespace pb {
 
-static constexpr int kGroup = 8;  // buckets per running-sum group in the reduction
+static constexpr int kGroup = 8;
+static constexpr unsigned kHeavy = 512;  // buckets longer than this get a whole CTA (skewed scalar distributions)  // buckets per running-sum group in the reduction
 
 PB_D G1Affine ld_affine(const uint4* p, size_t i) {
   const uint4* q = p + 6 * i;
@@ -173,7 +174,8 @@ __global__ void k_msm_digits(const uint4* scalars, size_t n, size_t stride, int 
 // The same CTA also emits `order`: the bucket ids sorted by descending size (counting sort on the
 // clipped size), so that the threads of a warp in k_msm_accumulate get buckets of near-equal length
 // and the warp does not idle on its longest lane.
-__global__ void __launch_bounds__(1024) k_msm_scan(const unsigned* counts, unsigned* offsets, unsigned* order, unsigned nb) {
+__global__ void __launch_bounds__(1024) k_msm_scan(const unsigned* counts, unsigned* offsets, unsigned* order, unsigned* n_heavy,
+                                                   unsigned nb) {
   __shared__ unsigned sums[1024];
   __shared__ unsigned bins[1024];
   const unsigned b = blockIdx.x, tid = threadIdx.x;
@@ -212,6 +214,8 @@ __global__ void __launch_bounds__(1024) k_msm_scan(const unsigned* counts, unsig
     __syncthreads();
   }
   bins[tid] = sums[tid] - mine;  // exclusive start of each bin
+  // buckets are ordered largest first, so the heavy ones are order[0 .. n_heavy)
+  if (tid == 1022u - kHeavy) n_heavy[b] = sums[tid];  // bins 0 .. 1022-kHeavy hold the sizes > kHeavy
   __syncthreads();
   for (unsigned k = tid; k < nb; k += 1024) {
     const unsigned pos = atomicAdd(&bins[1023u - min(cnt[k], 1023u)], 1u);
@@ -249,12 +253,14 @@ PB_D G1Xyzz shfl_down_xyzz(const G1Xyzz& p, int delta, int width) {
 // ([batch][nb]).  Buckets are visited in `order` (largest first, near-equal sizes per warp).
 template <int MIN_CTAS>
 __global__ void __launch_bounds__(128, MIN_CTAS) k_msm_accumulate(const uint4* table, const unsigned* sorted,
-                                                               const unsigned* offsets, const unsigned* order, unsigned nb,
-                                                               int log_split, size_t cap, uint4* sums) {
+                                                               const unsigned* offsets, const unsigned* order,
+                                                               const unsigned* n_heavy, unsigned nb, int log_split, size_t cap,
+                                                               uint4* sums) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned split = 1u << log_split;
-  const bool valid = t < ((size_t)nb << log_split);
   const unsigned b = blockIdx.y;
+  // the first n_heavy buckets of `order` are handled by k_msm_accumulate_heavy
+  const bool valid = t < ((size_t)nb << log_split) && (t >> log_split) >= n_heavy[b];
   const unsigned part = (unsigned)t & (split - 1);
   unsigned bucket = 0, lo = 0, hi = 0;
   if (valid) {
@@ -291,6 +297,46 @@ __global__ void __launch_bounds__(128, MIN_CTAS) k_msm_accumulate(const uint4* t
     xyzz_add(acc, o);
   }
   if (valid && part == 0) st_xyzz(sums, (size_t)b * nb + bucket, acc);
+}
+
+// Buckets longer than kHeavy (skewed scalars: many equal coefficients, 0/1 vectors, ...): one CTA per
+// bucket, strided over its entries, then a CTA-wide tree.  With uniformly random scalars n_heavy is 0
+// and the CTAs exit at once.
+__global__ void __launch_bounds__(128) k_msm_accumulate_heavy(const uint4* table, const unsigned* sorted, const unsigned* offsets,
+                                                              const unsigned* order, const unsigned* n_heavy, unsigned nb, size_t cap,
+                                                              uint4* sums) {
+  __shared__ uint4 sh[4 * 12];
+  const unsigned b = blockIdx.y;
+  const unsigned nh = n_heavy[b];
+  const unsigned* src = sorted + (size_t)b * cap;
+  const unsigned* off = offsets + (size_t)b * (nb + 1);
+  for (unsigned h = blockIdx.x; h < nh; h += gridDim.x) {
+    const unsigned bucket = order[(size_t)b * nb + h];
+    const unsigned start = off[bucket], end = off[bucket + 1];
+    G1Xyzz acc = G1Xyzz::identity();
+    for (unsigned k = start + threadIdx.x; k < end; k += 128) {
+      const unsigned e = __ldg(src + k);
+      G1Affine p = ld_affine(table, e >> 1);
+      if (p.is_inf()) continue;
+      if (e & 1u) p.y = p.y.neg();
+      xyzz_madd(acc, p.x, p.y);
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+      G1Xyzz o = shfl_down_xyzz(acc, d, 32);
+      xyzz_add(acc, o);
+    }
+    if ((threadIdx.x & 31) == 0) st_xyzz(sh, threadIdx.x >> 5, acc);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      G1Xyzz r = ld_xyzz(sh, 0);
+      for (int w = 1; w < 4; w++) {
+        G1Xyzz o = ld_xyzz(sh, w);
+        xyzz_add(r, o);
+      }
+      st_xyzz(sums, (size_t)b * nb + bucket, r);
+    }
+    __syncthreads();
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -509,6 +555,8 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
   PB_CUDA(cudaMallocAsync((void**)&counts, (size_t)batch * nb * 4, st));
   PB_CUDA(cudaMallocAsync((void**)&offsets, (size_t)batch * (nb + 1) * 4, st));
   PB_CUDA(cudaMallocAsync((void**)&order, (size_t)batch * nb * 4, st));
+  unsigned* n_heavy = nullptr;
+  PB_CUDA(cudaMallocAsync((void**)&n_heavy, (size_t)batch * 4, st));
   PB_CUDA(cudaMallocAsync((void**)&ebkt, (size_t)batch * cap * 4, st));
   PB_CUDA(cudaMallocAsync((void**)&epos, (size_t)batch * cap * 4, st));
   PB_CUDA(cudaMallocAsync((void**)&sorted, (size_t)batch * cap * 4, st));
@@ -521,7 +569,7 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
 
   PB_LAUNCH(k_msm_digits, dim3(div_up(n, 128), batch), 128, 0, st, (const uint4*)d_scalars, n, stride, c, W, nb,
             counts, ebkt, epos);
-  PB_LAUNCH(k_msm_scan, batch, 1024, 0, st, counts, offsets, order, nb);
+  PB_LAUNCH(k_msm_scan, batch, 1024, 0, st, counts, offsets, order, n_heavy, nb);
   PB_LAUNCH(k_msm_scatter, dim3(div_up(n, 256), W, batch), 256, 0, st, ebkt, epos, offsets, n, W, nb,
             srs->n_points, first, sorted);
   const bool prof = g_prof_on.load(std::memory_order_relaxed) != 0;
@@ -538,17 +586,18 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
     }();
     const dim3 grid(div_up((size_t)nb << log_split, 128), batch);
     if (min_ctas >= 4)
-      PB_LAUNCH(k_msm_accumulate<4>, grid, 128, 0, st, srs->table, sorted, offsets, order, nb, log_split, cap, sums);
+      PB_LAUNCH(k_msm_accumulate<4>, grid, 128, 0, st, srs->table, sorted, offsets, order, n_heavy, nb, log_split, cap, sums);
     else if (min_ctas == 3)
-      PB_LAUNCH(k_msm_accumulate<3>, grid, 128, 0, st, srs->table, sorted, offsets, order, nb, log_split, cap, sums);
+      PB_LAUNCH(k_msm_accumulate<3>, grid, 128, 0, st, srs->table, sorted, offsets, order, n_heavy, nb, log_split, cap, sums);
     else
-      PB_LAUNCH(k_msm_accumulate<2>, grid, 128, 0, st, srs->table, sorted, offsets, order, nb, log_split, cap, sums);
+      PB_LAUNCH(k_msm_accumulate<2>, grid, 128, 0, st, srs->table, sorted, offsets, order, n_heavy, nb, log_split, cap, sums);
   }
   std::vector<unsigned> h_tot(batch, 0);
   if (prof) {
     PB_CUDA(cudaEventRecord(ev1, st));
     PB_CUDA(cudaMemcpy2DAsync(h_tot.data(), 4, offsets + nb, (size_t)(nb + 1) * 4, 4, batch, cudaMemcpyDeviceToHost, st));
   }
+  PB_LAUNCH(k_msm_accumulate_heavy, dim3(64, batch), 128, 0, st, srs->table, sorted, offsets, order, n_heavy, nb, cap, sums);
   PB_LAUNCH(k_msm_groups, dim3(div_up(n_groups, 64), batch), 64, 0, st, (const uint4*)sums, nb, g, S, A);
   PB_LAUNCH(k_msm_group_classes, dim3(div_up(plan.nclasses, 4), batch), 128, 0, st, (const uint4*)S, (const uint4*)A, n_groups,
             plan, classes);
@@ -570,7 +619,7 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
   }
-  cudaFreeAsync(counts, st); cudaFreeAsync(offsets, st); cudaFreeAsync(order, st); cudaFreeAsync(ebkt, st);
+  cudaFreeAsync(counts, st); cudaFreeAsync(offsets, st); cudaFreeAsync(order, st); cudaFreeAsync(n_heavy, st); cudaFreeAsync(ebkt, st);
   cudaFreeAsync(epos, st); cudaFreeAsync(sorted, st); cudaFreeAsync(sums, st); cudaFreeAsync(classes, st);
   cudaFreeAsync(S, st); cudaFreeAsync(A, st); cudaFreeAsync(result, st);
 

@@ -189,3 +189,25 @@ def test_msm_2_20_points_against_known_secret(pb):
         check(lib().pb200_msm_g1_range(key._h, first, to_abi(poly[first : first + count]), count, out))
         parts.append(out.raw)
     assert pd.g1_sum(parts) == got.raw
+
+
+def test_msm_skewed_scalars_heavy_buckets(pb):
+    """Scalar distributions that put thousands of points into one bucket (the reference's rayon path
+    has no such cliff; ours routes buckets longer than 512 entries to whole CTAs)."""
+    import time
+
+    rng = random.Random(33)
+    n = 1 << 14
+    p0, step = rng.randrange(1, R.R_MOD), rng.randrange(1, R.R_MOD)
+    pts = progression_bases(n, p0, step)
+    key = pb.CommitKey(bases_to_abi(pts))
+    big = rng.randrange(R.R_MOD)
+    cases = [[big] * n, [rng.randrange(2) for _ in range(n)], [rng.choice([3, big, R.R_MOD - 1]) for _ in range(n)],
+             [big] * (n // 2) + rand_fr(rng, n // 2)]
+    t0 = time.time()
+    got = key.commit_batch([to_abi(s) for s in cases])
+    dt = time.time() - t0
+    for g, s in zip(got, cases):
+        k = sum(si * (p0 + i * step) for i, si in enumerate(s)) % R.R_MOD
+        assert R.g1_from_raw_bytes(g.raw) == R.g1_mul(R.G1_GEN, k)
+    assert dt < 5.0, f"skewed MSM took {dt:.2f}s"
