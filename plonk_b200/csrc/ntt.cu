@@ -133,8 +133,9 @@ __global__ void __launch_bounds__(kNttThreads) k_ntt_pass(PassArgs a) {
   }
   __syncthreads();
 
-  // log R radix-2 decimation-in-frequency stages: natural order in, bit-reversed order out.
-  for (int s = 0; s < a.r; s++) {
+  // log R radix-2 decimation-in-frequency stages: natural order in, bit-reversed order out.  The last
+  // stage (twiddle 1: a bare add/sub pair) is fused into the store phase below.
+  for (int s = 0; s + 1 < a.r; s++) {
     const int log_half = a.r - s - 1;
     const int half = 1 << log_half;
     for (int b = tid; b < (tile >> 1); b += kNttThreads) {
@@ -152,31 +153,50 @@ __global__ void __launch_bounds__(kNttThreads) k_ntt_pass(PassArgs a) {
     __syncthreads();
   }
 
-  if (!a.last) {
-    const size_t half_m = (size_t)1 << (a.r + a.log_lo - 1);
+  if (a.r == 0) {  // radix 1: nothing to transform (n = 1, or a degenerate plan)
     for (int idx = tid; idx < tile; idx += kNttThreads) {
-      const int k = idx >> a.log_t, t = idx & (T - 1);
-      const int kr = (a.r == 0) ? 0 : (int)(__brev((unsigned)k) >> (32 - a.r));
-      Fr v = lds_fr(S0, S1, (kr << a.log_t) + t);
-      const size_t e = (size_t)k * (lo0 + t);
-      Fr tw;
-      if (e < half_m) {
-        tw = ld_fr(a.w_m, e);
+      Fr v = lds_fr(S0, S1, idx);
+      size_t o;
+      if (!a.last) {
+        o = base + idx;
       } else {
-        tw = ld_fr(a.w_m, e - half_m).neg();
+        o = (k0b + idx) + (mid << a.log_r0);
+        if (a.post) v = v * ld_fr(a.post, o);
+        if (a.has_scalar) v = v * a.scalar;
       }
-      v = v * tw;
-      st_fr(out, base + ((size_t)k << a.log_lo) + t, v);
-    }
-  } else {
-    for (int idx = tid; idx < tile; idx += kNttThreads) {
-      const int k = idx >> a.log_t, t = idx & (T - 1);
-      const int kr = (a.r == 0) ? 0 : (int)(__brev((unsigned)k) >> (32 - a.r));
-      Fr v = lds_fr(S0, S1, (kr << a.log_t) + t);
-      const size_t o = (k0b + t) + (mid << a.log_r0) + ((size_t)k << a.log_h);
-      if (a.post) v = v * ld_fr(a.post, o);
-      if (a.has_scalar) v = v * a.scalar;
       st_fr(out, o, v);
+    }
+    return;
+  }
+
+  // Store phase with the last butterfly stage fused in: smem rows 2m and 2m+1 hold the operands of
+  // outputs k0 = bitrev(2m) (< R/2) and k0 + R/2.
+  const int half_r = R >> 1;
+  const size_t half_m = a.last ? 0 : ((size_t)1 << (a.r + a.log_lo - 1));
+  for (int idx = tid; idx < (tile >> 1); idx += kNttThreads) {
+    const int m = idx >> a.log_t, t = idx & (T - 1);
+    const Fr x = lds_fr(S0, S1, ((2 * m) << a.log_t) + t), y = lds_fr(S0, S1, ((2 * m + 1) << a.log_t) + t);
+    const int k0 = (int)(__brev((unsigned)(2 * m)) >> (32 - a.r));
+    Fr v[2] = {x + y, x - y};
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int k = k0 + u * half_r;
+      if (!a.last) {
+        const size_t e = (size_t)k * (lo0 + t);
+        Fr tw;
+        if (e < half_m) {
+          tw = ld_fr(a.w_m, e);
+        } else {
+          tw = ld_fr(a.w_m, e - half_m).neg();
+        }
+        st_fr(out, base + ((size_t)k << a.log_lo) + t, v[u] * tw);
+      } else {
+        const size_t o = (k0b + t) + (mid << a.log_r0) + ((size_t)k << a.log_h);
+        Fr r = v[u];
+        if (a.post) r = r * ld_fr(a.post, o);
+        if (a.has_scalar) r = r * a.scalar;
+        st_fr(out, o, r);
+      }
     }
   }
 }
