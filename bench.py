@@ -134,8 +134,13 @@ def run_ours(args):
             check(L.pb200_prove(prover._h, host_wit[slot].data_ptr(), n_wit, pi_idx, pi_vals, n_pi, bl, proofs[slot]))
 
     def run_steps(k, resident, base=0):
-        for s in range(k):
-            list(pool.map(lambda slot: one(slot, base + s, resident), range(inflight)))
+        # k steps = k proofs on each of the `inflight` slots; the slots run back to back without a
+        # barrier between steps (independent proofs: nothing to wait for)
+        def worker(slot):
+            for s in range(k):
+                one(slot, base + s, resident)
+
+        list(pool.map(worker, range(inflight)))
 
     def barrier():
         torch.cuda.synchronize()
@@ -231,9 +236,11 @@ def run_ours(args):
     finish_dist(world)
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_msm_accumulate launch (batch 4, 2^16 points) from the
-# committed ncu capture under profiles/; None until a capture exists.
-TRAFFIC_PER_LAUNCH = None
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_msm_accumulate launch (batch of 4 MSMs over 2^16+7
+# points: 364.9 MB + 22.9 MB) from the committed capture profiles/ncu_r01_accumulate.ncu-rep.  The
+# algorithmic 128 B/point would be 33.6 MB: the x11.5 is the deliberate table of window multiples
+# (16 x 96 B gathered per point), not a re-read to fix.
+TRAFFIC_PER_LAUNCH = 387.8e6
 
 
 def ntt_microbench(L, torch, imad_peak):

@@ -16,6 +16,16 @@ std::atomic<uint64_t> g_launches{0};
 static std::mutex g_init_mu;
 static int g_device = -1;
 
+// Per-call workspaces come from the stream-ordered pool; keep freed blocks cached instead of
+// returning them to the driver at every synchronisation.
+static void keep_pool(int device) {
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+}
+
 int ensure_init() {
   std::lock_guard<std::mutex> lk(g_init_mu);
   if (g_device >= 0) {
@@ -28,6 +38,7 @@ int ensure_init() {
   int dev = 0;
   PB_CUDA(cudaGetDevice(&dev));
   g_device = dev;
+  keep_pool(dev);
   return 0;
 }
 
@@ -40,9 +51,9 @@ cudaStream_t thread_stream() {
 }
 
 int ntt_run(const uint64_t* d_in, size_t in_len, uint64_t* d_out, uint32_t log_n, int inverse, int coset,
-            uint32_t batch, size_t in_stride, size_t out_stride, cudaStream_t st);
+            uint32_t batch, size_t in_stride, size_t out_stride, cudaStream_t st, Arena* ar);
 int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_t n, uint32_t batch,
-            size_t stride, uint64_t* out_affine_host, cudaStream_t st);
+            size_t stride, uint64_t* out_affine_host, cudaStream_t st, Arena* ar);
 int srs_upload(const uint8_t* raw, size_t n_points, pb200_srs** out);
 int selftest_mul(int which, const uint64_t* a, const uint64_t* b, uint64_t* o, size_t n);
 int imad_peak(double* out);
@@ -66,12 +77,7 @@ int pb200_init(int device) {
     PB_CUDA(cudaSetDevice(device));
     g_device = device;
   }
-  // raise the stream-ordered pool's release threshold so per-call workspaces are recycled
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-    uint64_t thr = ~0ull;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-  }
+  keep_pool(device);
   return 0;
 }
 
@@ -89,7 +95,7 @@ int pb200_ntt_dev(const uint64_t* d_in, size_t in_len, uint64_t* d_out, uint32_t
                   uint32_t batch, size_t in_stride, size_t out_stride, void* stream) {
   PB_TRY(ensure_init());
   cudaStream_t st = stream ? (cudaStream_t)stream : thread_stream();
-  return ntt_run(d_in, in_len, d_out, log_n, inverse, coset, batch, in_stride, out_stride, st);
+  return ntt_run(d_in, in_len, d_out, log_n, inverse, coset, batch, in_stride, out_stride, st, nullptr);
 }
 
 int pb200_ntt(const uint64_t* in, size_t in_len, uint64_t* out, uint32_t log_n, int inverse, int coset,
@@ -107,7 +113,7 @@ int pb200_ntt(const uint64_t* in, size_t in_len, uint64_t* out, uint32_t log_n, 
     PB_CUDA(cudaMallocAsync((void**)&d_in, (size_t)batch * use * 32, st));
     PB_CUDA(cudaMemcpy2DAsync(d_in, use * 32, in, in_stride * 32, use * 32, batch, cudaMemcpyHostToDevice, st));
   }
-  int rc = ntt_run(d_in, use, d_out, log_n, inverse, coset, batch, use, n, st);
+  int rc = ntt_run(d_in, use, d_out, log_n, inverse, coset, batch, use, n, st, nullptr);
   if (rc == 0) {
     cudaError_t e = cudaMemcpy2DAsync(out, out_stride * 32, d_out, n * 32, n * 32, batch, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -133,7 +139,7 @@ int pb200_msm_g1_dev(const pb200_srs_t* srs, const uint64_t* d_scalars, size_t n
   PB_TRY(ensure_init());
   if (!srs || !out_affine_host) return fail(PB200_ERR_INVALID_ARG, "null argument");
   cudaStream_t st = stream ? (cudaStream_t)stream : thread_stream();
-  return msm_run(srs, 0, d_scalars, n_scalars, batch, stride, out_affine_host, st);
+  return msm_run(srs, 0, d_scalars, n_scalars, batch, stride, out_affine_host, st, nullptr);
 }
 
 static int msm_host(const pb200_srs_t* srs, size_t first, const uint64_t* scalars, size_t n, uint32_t batch,
@@ -147,7 +153,7 @@ static int msm_host(const pb200_srs_t* srs, size_t first, const uint64_t* scalar
     PB_CUDA(cudaMallocAsync((void**)&d, (size_t)batch * n * 32, st));
     PB_CUDA(cudaMemcpy2DAsync(d, n * 32, scalars, stride * 32, n * 32, batch, cudaMemcpyHostToDevice, st));
   }
-  int rc = msm_run(srs, first, d, n, batch, n, out, st);
+  int rc = msm_run(srs, first, d, n, batch, n, out, st, nullptr);
   if (d) cudaFreeAsync(d, st);
   return rc;
 }

@@ -49,4 +49,37 @@ int ensure_init();
 
 inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
+// Bump allocator over one device allocation.  A proof draws all its scratch from an arena owned by
+// the prover (one per in-flight proof), so the steady state makes no allocator calls at all; callers
+// without an arena (the stand-alone NTT / MSM entry points) use the stream-ordered pool instead.
+// Everything carved from an arena is used on a single stream, so reusing memory after `reset` is
+// ordered by the stream itself.
+struct Arena {
+  char* base = nullptr;
+  size_t size = 0, off = 0;
+  void* take(size_t bytes) {
+    const size_t a = (off + 255) & ~(size_t)255;
+    if (a + bytes > size) return nullptr;
+    off = a + bytes;
+    return base + a;
+  }
+  size_t mark() const { return off; }
+  void reset(size_t m) { off = m; }
+};
+
+// ptr = arena block or stream-ordered allocation
+#define PB_ALLOC(ptr, bytes, st, ar)                                                        \
+  do {                                                                                      \
+    if (ar) {                                                                               \
+      *(void**)&(ptr) = (ar)->take(bytes);                                                  \
+      if (!(ptr)) return pb::fail(PB200_ERR_CUDA, "workspace arena exhausted", #ptr);       \
+    } else {                                                                                \
+      PB_CUDA(cudaMallocAsync((void**)&(ptr), (bytes), (st)));                              \
+    }                                                                                       \
+  } while (0)
+#define PB_FREE(ptr, st, ar)                 \
+  do {                                       \
+    if (!(ar) && (ptr)) cudaFreeAsync((ptr), (st)); \
+  } while (0)
+
 }  // namespace pb

@@ -507,7 +507,7 @@ static void xyzz_dev_to_host(const uint32_t* w, pbh::HXyzz* o) {
 }
 
 int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_t n, uint32_t batch,
-            size_t stride, uint64_t* out_affine_host, cudaStream_t st) {
+            size_t stride, uint64_t* out_affine_host, cudaStream_t st, Arena* ar) {
   if (first + n > srs->n_points) return fail(PB200_ERR_DEGREE_TOO_LARGE, "more scalars than commit-key points");
   if (batch == 0) return 0;
   if (n == 0) {
@@ -550,21 +550,22 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
     if (plan.ndig > 7) return fail(PB200_ERR_INVALID_ARG, "window too wide for the bucket reduction");
   }
 
+  const size_t ar_mark = ar ? ar->mark() : 0;
   unsigned *counts = nullptr, *offsets = nullptr, *order = nullptr, *ebkt = nullptr, *epos = nullptr, *sorted = nullptr;
   uint4 *sums = nullptr, *classes = nullptr, *S = nullptr, *A = nullptr, *result = nullptr;
-  PB_CUDA(cudaMallocAsync((void**)&counts, (size_t)batch * nb * 4, st));
-  PB_CUDA(cudaMallocAsync((void**)&offsets, (size_t)batch * (nb + 1) * 4, st));
-  PB_CUDA(cudaMallocAsync((void**)&order, (size_t)batch * nb * 4, st));
+  PB_ALLOC(counts, (size_t)batch * nb * 4, st, ar);
+  PB_ALLOC(offsets, (size_t)batch * (nb + 1) * 4, st, ar);
+  PB_ALLOC(order, (size_t)batch * nb * 4, st, ar);
   unsigned* n_heavy = nullptr;
-  PB_CUDA(cudaMallocAsync((void**)&n_heavy, (size_t)batch * 4, st));
-  PB_CUDA(cudaMallocAsync((void**)&ebkt, (size_t)batch * cap * 4, st));
-  PB_CUDA(cudaMallocAsync((void**)&epos, (size_t)batch * cap * 4, st));
-  PB_CUDA(cudaMallocAsync((void**)&sorted, (size_t)batch * cap * 4, st));
-  PB_CUDA(cudaMallocAsync((void**)&sums, (size_t)batch * nb * 192, st));
-  PB_CUDA(cudaMallocAsync((void**)&classes, (size_t)batch * plan.nclasses * 192, st));
-  PB_CUDA(cudaMallocAsync((void**)&S, (size_t)batch * n_groups * 192, st));
-  PB_CUDA(cudaMallocAsync((void**)&A, (size_t)batch * n_groups * 192, st));
-  PB_CUDA(cudaMallocAsync((void**)&result, (size_t)batch * (plan.ndig + 1) * 192, st));
+  PB_ALLOC(n_heavy, (size_t)batch * 4, st, ar);
+  PB_ALLOC(ebkt, (size_t)batch * cap * 4, st, ar);
+  PB_ALLOC(epos, (size_t)batch * cap * 4, st, ar);
+  PB_ALLOC(sorted, (size_t)batch * cap * 4, st, ar);
+  PB_ALLOC(sums, (size_t)batch * nb * 192, st, ar);
+  PB_ALLOC(classes, (size_t)batch * plan.nclasses * 192, st, ar);
+  PB_ALLOC(S, (size_t)batch * n_groups * 192, st, ar);
+  PB_ALLOC(A, (size_t)batch * n_groups * 192, st, ar);
+  PB_ALLOC(result, (size_t)batch * (plan.ndig + 1) * 192, st, ar);
   PB_CUDA(cudaMemsetAsync(counts, 0, (size_t)batch * nb * 4, st));
 
   PB_LAUNCH(k_msm_digits, dim3(div_up(n, 128), batch), 128, 0, st, (const uint4*)d_scalars, n, stride, c, W, nb,
@@ -619,9 +620,13 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
   }
-  cudaFreeAsync(counts, st); cudaFreeAsync(offsets, st); cudaFreeAsync(order, st); cudaFreeAsync(n_heavy, st); cudaFreeAsync(ebkt, st);
-  cudaFreeAsync(epos, st); cudaFreeAsync(sorted, st); cudaFreeAsync(sums, st); cudaFreeAsync(classes, st);
-  cudaFreeAsync(S, st); cudaFreeAsync(A, st); cudaFreeAsync(result, st);
+  if (ar) {
+    ar->reset(ar_mark);  // the stream was synchronised above: the scratch is dead
+  } else {
+    cudaFreeAsync(counts, st); cudaFreeAsync(offsets, st); cudaFreeAsync(order, st); cudaFreeAsync(n_heavy, st); cudaFreeAsync(ebkt, st);
+    cudaFreeAsync(epos, st); cudaFreeAsync(sorted, st); cudaFreeAsync(sums, st); cudaFreeAsync(classes, st);
+    cudaFreeAsync(S, st); cudaFreeAsync(A, st); cudaFreeAsync(result, st);
+  }
 
   // Host tail: R = sum A_G + g * sum_j 2^shift_j D_j (Horner over the digits), then the affine
   // normalisation of Commitment::from (commitment.rs:89-93) with one shared inversion per batch
@@ -662,6 +667,21 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
     }
   }
   return 0;
+}
+
+// Upper bound of the arena bytes one msm_run(n, batch) call takes (same list as the PB_ALLOCs above).
+size_t msm_workspace_bytes(const pb200_srs* srs, size_t n, uint32_t batch) {
+  const size_t nb = (size_t)1 << (srs->c - 1), cap = n * (size_t)srs->W;
+  const size_t n_groups = std::max<size_t>(1, nb / kGroup);
+  size_t b = 0;
+  b += 3 * ((size_t)batch * (nb + 1) * 4 + 256);      // counts, offsets, order
+  b += (size_t)batch * 4 + 256;                        // n_heavy
+  b += 3 * ((size_t)batch * cap * 4 + 256);            // ebkt, epos, sorted
+  b += (size_t)batch * nb * 192 + 256;                 // sums
+  b += 2 * ((size_t)batch * n_groups * 192 + 256);     // S, A
+  b += (size_t)batch * (8 * 16 + n_groups / 256 + 2) * 192 + 256;  // classes
+  b += (size_t)batch * 9 * 192 + 256;                  // result
+  return b + 4096;
 }
 
 int srs_upload(const uint8_t* raw, size_t n_points, pb200_srs** out) {

@@ -355,7 +355,7 @@ static void ntt_plan(int L, int* radices, int* n_pass) {
 }
 
 int ntt_run(const uint64_t* d_in, size_t in_len, uint64_t* d_out, uint32_t log_n, int inverse,
-            int coset, uint32_t batch, size_t in_stride, size_t out_stride, cudaStream_t st) {
+            int coset, uint32_t batch, size_t in_stride, size_t out_stride, cudaStream_t st, Arena* ar) {
   if (log_n >= 32) return fail(PB200_ERR_INVALID_DOMAIN, "log_n >= TWO_ADACITY");
   if (batch == 0) return 0;
   static std::once_flag once;
@@ -382,7 +382,8 @@ int ntt_run(const uint64_t* d_in, size_t in_len, uint64_t* d_out, uint32_t log_n
   // pass writes the caller's buffer.  (A single pass is one CTA per vector: loads finish before
   // stores begin, so in == out is fine there.)
   uint64_t* d_tmp = nullptr;
-  if (n_pass > 1) PB_CUDA(cudaMallocAsync((void**)&d_tmp, (size_t)batch * n * 32, st));
+  const size_t ar_mark = ar ? ar->mark() : 0;
+  if (n_pass > 1) PB_ALLOC(d_tmp, (size_t)batch * n * 32, st, ar);
 
   int log_h = 0;
   for (int q = 0; q < n_pass; q++) {
@@ -424,7 +425,8 @@ int ntt_run(const uint64_t* d_in, size_t in_len, uint64_t* d_out, uint32_t log_n
     PB_CUDA(cudaGetLastError());
     log_h += a.r;
   }
-  if (d_tmp) PB_CUDA(cudaFreeAsync(d_tmp, st));
+  PB_FREE(d_tmp, st, ar);
+  if (ar) ar->reset(ar_mark);  // later users of this memory are ordered behind these kernels by the stream
   return 0;
 }
 

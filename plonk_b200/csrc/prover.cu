@@ -18,6 +18,7 @@
 // The Fiat-Shamir transcript (transcript.h) and a handful of scalar formulas run on the host
 // between rounds.
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -29,9 +30,10 @@ struct pb200_srs;
 namespace pb {
 
 int ntt_run(const uint64_t* d_in, size_t in_len, uint64_t* d_out, uint32_t log_n, int inverse, int coset,
-            uint32_t batch, size_t in_stride, size_t out_stride, cudaStream_t st);
+            uint32_t batch, size_t in_stride, size_t out_stride, cudaStream_t st, Arena* ar);
 int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_t n, uint32_t batch,
-            size_t stride, uint64_t* out_affine_host, cudaStream_t st);
+            size_t stride, uint64_t* out_affine_host, cudaStream_t st, Arena* ar);
+size_t msm_workspace_bytes(const pb200_srs* srs, size_t n, uint32_t batch);
 int srs_upload(const uint8_t* raw, size_t n_points, pb200_srs** out);
 void srs_free(pb200_srs* s);
 size_t srs_len(const pb200_srs* s);
@@ -463,6 +465,11 @@ struct pb200_prover {
   int has_widget[4] = {0, 0, 0, 0};
   uint8_t comm[pb::N_POLY][48];
   size_t n_witnesses = 0;
+  // scratch arenas, one per proof in flight (allocated on first use, then recycled)
+  mutable std::mutex ws_mu;
+  mutable std::vector<pb::Arena> ws_free;
+  mutable std::vector<char*> ws_all;
+  size_t ws_bytes = 0;
 };
 
 namespace pb {
@@ -480,11 +487,12 @@ static HFr to_host(const Fr& x) {
 static HFr hfr_pow(const HFr& x, uint64_t e) { return x.pow(&e, 1); }
 
 template <bool MUL, bool REV>
-static int fr_scan(const uint4* in, size_t n, uint4* out, cudaStream_t st) {
+static int fr_scan(const uint4* in, size_t n, uint4* out, cudaStream_t st, Arena* ar) {
   const unsigned nblk = div_up(n, 2048);
   uint4 *tot = nullptr, *tot_scan = nullptr;
-  PB_CUDA(cudaMallocAsync((void**)&tot, (size_t)nblk * 32, st));
-  PB_CUDA(cudaMallocAsync((void**)&tot_scan, (size_t)nblk * 32, st));
+  const size_t ar_mark = ar ? ar->mark() : 0;
+  PB_ALLOC(tot, (size_t)nblk * 32, st, ar);
+  PB_ALLOC(tot_scan, (size_t)nblk * 32, st, ar);
   PB_LAUNCH((k_scan_local<MUL, REV>), nblk, 256, 0, st, in, n, out, tot);
   if (nblk > 1) {
     if (nblk > 2048) return fail(PB200_ERR_INVALID_ARG, "scan too large");
@@ -492,8 +500,9 @@ static int fr_scan(const uint4* in, size_t n, uint4* out, cudaStream_t st) {
     PB_LAUNCH((k_scan_fixup<MUL, REV>), div_up(n, 256), 256, 0, st, out, n, (const uint4*)tot_scan);
   }
   PB_CUDA(cudaGetLastError());
-  cudaFreeAsync(tot, st);
-  cudaFreeAsync(tot_scan, st);
+  PB_FREE(tot, st, ar);
+  PB_FREE(tot_scan, st, ar);
+  if (ar) ar->reset(ar_mark);
   return 0;
 }
 
@@ -570,23 +579,23 @@ int prover_new(const uint8_t* label, size_t label_len, size_t constraints, const
     PB_CUDA(cudaStreamSynchronize(st));  // sig (host vector) must outlive the copy
     cudaFreeAsync(d_sig, st);
   }
-  PB_TRY(ntt_run((const uint64_t*)cols, n, (uint64_t*)P->d_polys, log_n, 1, 0, N_POLY, n, n, st));
+  PB_TRY(ntt_run((const uint64_t*)cols, n, (uint64_t*)P->d_polys, log_n, 1, 0, N_POLY, n, n, st, nullptr));
   // commitments (compiler.rs:213-232): an all-zero selector commits to the identity
   {
     std::vector<uint64_t> aff((size_t)N_POLY * 12);
-    PB_TRY(msm_run(P->srs, 0, (const uint64_t*)P->d_polys, n, N_POLY, n, aff.data(), st));
+    PB_TRY(msm_run(P->srs, 0, (const uint64_t*)P->d_polys, n, N_POLY, n, aff.data(), st, nullptr));
     for (int k = 0; k < N_POLY; k++) compress_affine(aff.data() + 12 * k, P->comm[k]);
     const int widget_sel[4] = {Q_RANGE, Q_LOGIC, Q_FIXED, Q_VAR};
     for (int w = 0; w < 4; w++) P->has_widget[w] = (P->comm[widget_sel[w]][0] & 0x40) ? 0 : 1;
   }
   // coset evaluations over 8n (compiler.rs:306-377)
-  PB_TRY(ntt_run((const uint64_t*)P->d_polys, n, (uint64_t*)P->d_key8, log_n + 3, 0, 1, N_POLY, n, n8, st));
+  PB_TRY(ntt_run((const uint64_t*)P->d_polys, n, (uint64_t*)P->d_key8, log_n + 3, 0, 1, N_POLY, n, n8, st, nullptr));
   {
     HFr lin[2] = {HFr::zero(), HFr::one()};
     uint4* d_lin = nullptr;
     PB_CUDA(cudaMallocAsync((void**)&d_lin, 64, st));
     PB_CUDA(cudaMemcpyAsync(d_lin, lin, 64, cudaMemcpyHostToDevice, st));
-    PB_TRY(ntt_run((const uint64_t*)d_lin, 2, (uint64_t*)P->d_linear8, log_n + 3, 0, 1, 1, 2, n8, st));
+    PB_TRY(ntt_run((const uint64_t*)d_lin, 2, (uint64_t*)P->d_linear8, log_n + 3, 0, 1, 1, 2, n8, st, nullptr));
     PB_CUDA(cudaStreamSynchronize(st));
     cudaFreeAsync(d_lin, st);
   }
@@ -609,10 +618,17 @@ int prover_new(const uint8_t* label, size_t label_len, size_t constraints, const
     PB_LAUNCH(k_scale_period8, div_up(n8, 256), 256, 0, st, P->d_l1_8, n8, c);
   }
   // sigma evaluations over n (prover.rs:95-100)
-  PB_TRY(ntt_run((const uint64_t*)(P->d_polys + 2 * (size_t)S1 * n), n, (uint64_t*)P->d_sigma, log_n, 0, 0, 4, n, n, st));
+  PB_TRY(ntt_run((const uint64_t*)(P->d_polys + 2 * (size_t)S1 * n), n, (uint64_t*)P->d_sigma, log_n, 0, 0, 4, n, n, st, nullptr));
   PB_CUDA(cudaGetLastError());
   PB_CUDA(cudaStreamSynchronize(st));
   cudaFreeAsync(cols, st);
+  {  // arena size for one proof: prover scratch + the larger of (NTT scratch, MSM scratch)
+    const size_t stride = n + 8;
+    const size_t elems = 8 * n + 15 * stride + 64 * n + 64 + 16 * (size_t)div_up(stride, 2048) + 4 * (size_t)div_up(stride, 2048);
+    const size_t ntt_tmp = 5 * n8 * 32;
+    const size_t msm_ws = msm_workspace_bytes(P->srs, std::min(stride, srs_len(P->srs)), 4);
+    P->ws_bytes = elems * 32 + std::max(ntt_tmp, msm_ws) + (size_t)64 * 256 + (1 << 20);
+  }
   *out = P;
   return 0;
 }
@@ -621,6 +637,7 @@ void prover_free(pb200_prover* P) {
   if (!P) return;
   if (P->srs) srs_free(P->srs);
   cudaFree(P->d_wires); cudaFree(P->d_polys); cudaFree(P->d_key8); cudaFree(P->d_linear8); cudaFree(P->d_l1_8); cudaFree(P->d_sigma);
+  for (char* w : P->ws_all) cudaFree(w);
   delete P;
 }
 
@@ -650,35 +667,55 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
   const uint4* w_half = nullptr;
   PB_TRY(get_twiddles(log_n, false, st, &w_half));
 
-  // workspace
+  // workspace: one arena per proof in flight
+  Arena arena;
+  {
+    std::lock_guard<std::mutex> lk(P->ws_mu);
+    if (!P->ws_free.empty()) {
+      arena = P->ws_free.back();
+      P->ws_free.pop_back();
+    }
+  }
+  if (!arena.base) {
+    char* mem = nullptr;
+    PB_CUDA(cudaMalloc((void**)&mem, P->ws_bytes));
+    arena.base = mem;
+    arena.size = P->ws_bytes;
+    std::lock_guard<std::mutex> lk(P->ws_mu);
+    P->ws_all.push_back(mem);
+  }
+  arena.off = 0;
+  struct Release {
+    const pb200_prover* P;
+    Arena* a;
+    cudaStream_t st;
+    ~Release() {
+      cudaStreamSynchronize(st);  // error paths may leave work in flight
+      a->off = 0;
+      std::lock_guard<std::mutex> lk(P->ws_mu);
+      P->ws_free.push_back(*a);
+    }
+  } release{P, &arena, st};
+  Arena* ar = &arena;
   uint4 *wv, *wp, *zp, *num, *den, *w8, *quot, *tcoef, *tq, *pi_dense, *agg, *pw, *scratch, *evals_d, *partial;
   unsigned* flag;
   const unsigned eval_blocks = div_up(stride, 2048);
-  PB_CUDA(cudaMallocAsync((void**)&wv, 4 * n * 32, st));
-  PB_CUDA(cudaMallocAsync((void**)&zp, 5 * stride * 32, st));  // [z, a, b, c, d], one coset-NTT batch in round 3
+  PB_ALLOC(wv, 4 * n * 32, st, ar);
+  PB_ALLOC(zp, 5 * stride * 32, st, ar);  // [z, a, b, c, d], one coset-NTT batch in round 3
   wp = zp + 2 * stride;
-  PB_CUDA(cudaMallocAsync((void**)&num, n * 32, st));
-  PB_CUDA(cudaMallocAsync((void**)&den, n * 32, st));
-  PB_CUDA(cudaMallocAsync((void**)&w8, 6 * n8 * 32, st));
-  PB_CUDA(cudaMallocAsync((void**)&quot, n8 * 32, st));
-  PB_CUDA(cudaMallocAsync((void**)&tcoef, n8 * 32, st));
-  PB_CUDA(cudaMallocAsync((void**)&tq, 4 * stride * 32, st));
-  PB_CUDA(cudaMallocAsync((void**)&pi_dense, 2 * n * 32, st));
-  PB_CUDA(cudaMallocAsync((void**)&agg, 2 * stride * 32, st));
-  PB_CUDA(cudaMallocAsync((void**)&pw, 2 * stride * 32, st));
-  PB_CUDA(cudaMallocAsync((void**)&scratch, 2 * stride * 32, st));
-  PB_CUDA(cudaMallocAsync((void**)&evals_d, 16 * 32, st));
-  PB_CUDA(cudaMallocAsync((void**)&partial, (size_t)16 * eval_blocks * 32, st));
-  PB_CUDA(cudaMallocAsync((void**)&flag, 4, st));
-  auto free_all = [&]() {
-    uint4* bufs[] = {wv, zp, num, den, w8, quot, tcoef, tq, pi_dense, agg, pw, scratch, evals_d, partial};
-    for (uint4* b : bufs) cudaFreeAsync(b, st);
-    cudaFreeAsync(flag, st);
-  };
-  struct Guard {
-    decltype(free_all)& f;
-    ~Guard() { f(); }
-  } guard{free_all};
+  PB_ALLOC(num, n * 32, st, ar);
+  PB_ALLOC(den, n * 32, st, ar);
+  PB_ALLOC(w8, 6 * n8 * 32, st, ar);
+  PB_ALLOC(quot, n8 * 32, st, ar);
+  PB_ALLOC(tcoef, n8 * 32, st, ar);
+  PB_ALLOC(tq, 4 * stride * 32, st, ar);
+  PB_ALLOC(pi_dense, 2 * n * 32, st, ar);
+  PB_ALLOC(agg, 2 * stride * 32, st, ar);
+  PB_ALLOC(pw, 2 * stride * 32, st, ar);
+  PB_ALLOC(scratch, 2 * stride * 32, st, ar);
+  PB_ALLOC(evals_d, 16 * 32, st, ar);
+  PB_ALLOC(partial, (size_t)16 * eval_blocks * 32, st, ar);
+  PB_ALLOC(flag, 4, st, ar);
 
   uint64_t aff[4 * 12];
   uint8_t c48[11][48];
@@ -686,7 +723,7 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
   // ---- round 1 -------------------------------------------------------------------------------
   PB_LAUNCH(k_gather_wires, dim3(div_up(n, 256), 4), 256, 0, st, (const uint4*)d_wit, (const uint32_t*)P->d_wires, P->constraints, n, wv);
   PB_CUDA(cudaMemsetAsync(wp, 0, 4 * stride * 32, st));
-  PB_TRY(ntt_run((const uint64_t*)wv, n, (uint64_t*)wp, log_n, 1, 0, 4, n, stride, st));
+  PB_TRY(ntt_run((const uint64_t*)wv, n, (uint64_t*)wp, log_n, 1, 0, 4, n, stride, st, ar));
   {
     BlindArgs ba;
     ba.nb = 2;
@@ -695,7 +732,7 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
       for (int i = 0; i < 2; i++) ba.b[p][i] = to_dev(BL[2 * p + i]);
     PB_LAUNCH(k_blind, 1, 32, 0, st, wp, stride, n, ba);
   }
-  PB_TRY(msm_run(P->srs, 0, (const uint64_t*)wp, n + 2, 4, stride, aff, st));
+  PB_TRY(msm_run(P->srs, 0, (const uint64_t*)wp, n + 2, 4, stride, aff, st, ar));
   for (int k = 0; k < 4; k++) compress_affine(aff + 12 * k, c48[k]);
   tr.append_commitment("a_comm", c48[0]);
   tr.append_commitment("b_comm", c48[1]);
@@ -708,9 +745,9 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
   const HFr gamma = tr.challenge_scalar("gamma");
   PB_LAUNCH(k_perm_terms, div_up(n, 128), 128, 0, st, (const uint4*)wv, (const uint4*)P->d_sigma, w_half, n, to_dev(beta), to_dev(gamma), num, den);
   PB_LAUNCH(k_batch_div, div_up(div_up(n, 8), 128), 128, 0, st, (const uint4*)num, (const uint4*)den, n, num);
-  PB_TRY((fr_scan<true, false>(num, n, den, st)));  // den <- permutation vector z[i] = prod_{j<i} num_j/den_j
+  PB_TRY((fr_scan<true, false>(num, n, den, st, ar)));  // den <- permutation vector z[i] = prod_{j<i} num_j/den_j
   PB_CUDA(cudaMemsetAsync(zp, 0, stride * 32, st));
-  PB_TRY(ntt_run((const uint64_t*)den, n, (uint64_t*)zp, log_n, 1, 0, 1, n, stride, st));
+  PB_TRY(ntt_run((const uint64_t*)den, n, (uint64_t*)zp, log_n, 1, 0, 1, n, stride, st, ar));
   {
     BlindArgs ba;
     ba.nb = 3;
@@ -718,7 +755,7 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
     for (int i = 0; i < 3; i++) ba.b[0][i] = to_dev(BL[8 + i]);
     PB_LAUNCH(k_blind, 1, 32, 0, st, zp, stride, n, ba);
   }
-  PB_TRY(msm_run(P->srs, 0, (const uint64_t*)zp, n + 3, 1, stride, aff, st));
+  PB_TRY(msm_run(P->srs, 0, (const uint64_t*)zp, n + 3, 1, stride, aff, st, ar));
   compress_affine(aff, c48[4]);
   tr.append_commitment("z_comm", c48[4]);
 
@@ -732,11 +769,11 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
   PB_CUDA(cudaMemsetAsync(pi_dense, 0, 2 * n * 32, st));
   for (size_t i = 0; i < n_pi; i++)
     PB_CUDA(cudaMemcpyAsync(pi_dense + 2 * pi_idx[i], PIV + i, 32, cudaMemcpyHostToDevice, st));
-  if (n_pi) PB_TRY(ntt_run((const uint64_t*)pi_dense, n, (uint64_t*)(pi_dense + 2 * n), log_n, 1, 0, 1, n, n, st));
+  if (n_pi) PB_TRY(ntt_run((const uint64_t*)pi_dense, n, (uint64_t*)(pi_dense + 2 * n), log_n, 1, 0, 1, n, n, st, ar));
   // coset evaluations: z, a, b, c, d, pi (quotient_poly.rs:50-59, 177)
-  PB_TRY(ntt_run((const uint64_t*)zp, n + 3, (uint64_t*)w8, log_n + 3, 0, 1, 5, stride, n8, st));
+  PB_TRY(ntt_run((const uint64_t*)zp, n + 3, (uint64_t*)w8, log_n + 3, 0, 1, 5, stride, n8, st, ar));
   if (n_pi)
-    PB_TRY(ntt_run((const uint64_t*)(pi_dense + 2 * n), n, (uint64_t*)(w8 + 2 * 5 * n8), log_n + 3, 0, 1, 1, n, n8, st));
+    PB_TRY(ntt_run((const uint64_t*)(pi_dense + 2 * n), n, (uint64_t*)(w8 + 2 * 5 * n8), log_n + 3, 0, 1, 1, n, n8, st, ar));
   else
     PB_CUDA(cudaMemsetAsync(w8 + 2 * 5 * n8, 0, n8 * 32, st));  // empty PI polynomial: 8n zeros
   {
@@ -748,7 +785,7 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
     q.has_range = P->has_widget[0]; q.has_logic = P->has_widget[1]; q.has_fixed = P->has_widget[2]; q.has_var = P->has_widget[3];
     PB_LAUNCH(k_quotient, div_up(n8, 128), 128, 0, st, q);
   }
-  PB_TRY(ntt_run((const uint64_t*)quot, n8, (uint64_t*)tcoef, log_n + 3, 1, 1, 1, n8, n8, st));
+  PB_TRY(ntt_run((const uint64_t*)quot, n8, (uint64_t*)tcoef, log_n + 3, 1, 1, 1, n8, n8, st, ar));
   // quotient_poly.len() > 7n  =>  CircuitUnsatisfied (quotient_poly.rs:132-134); coefficients past
   // 4n+7 cannot be committed with this key either
   PB_CUDA(cudaMemsetAsync(flag, 0, 4, st));
@@ -758,7 +795,7 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
   PB_CUDA(cudaMemcpyAsync(&h_flag, flag, 4, cudaMemcpyDeviceToHost, st));
   const size_t key_len = srs_len(P->srs);
   const size_t tlen = std::min(stride, key_len);
-  PB_TRY(msm_run(P->srs, 0, (const uint64_t*)tq, tlen, 4, stride, aff, st));  // synchronises the stream
+  PB_TRY(msm_run(P->srs, 0, (const uint64_t*)tq, tlen, 4, stride, aff, st, ar));  // synchronises the stream
   if (h_flag) return fail(PB200_ERR_UNSATISFIED, "CircuitUnsatisfied");
   for (int k = 0; k < 4; k++) compress_affine(aff + 12 * k, c48[5 + k]);
   tr.append_commitment("t_low_comm", c48[5]);
@@ -899,13 +936,13 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
       uint4* sc_w = scratch + 2 * (size_t)w * stride;
       PB_TRY(fill_powers(pw_w, stride, to_dev(pts[w]), Fr::one(), st));
       PB_LAUNCH(k_mul_pointwise, div_up(stride, 128), 128, 0, st, (const uint4*)c_w, (const uint4*)pw_w, stride, sc_w);
-      PB_TRY((fr_scan<false, true>(sc_w, stride, c_w, st)));  // exclusive suffix sums
+      PB_TRY((fr_scan<false, true>(sc_w, stride, c_w, st, ar)));  // exclusive suffix sums
       const HFr zi = pts[w].inv();
       PB_TRY(fill_powers(pw_w, stride, to_dev(zi), to_dev(zi), st));
       PB_LAUNCH(k_mul_pointwise, div_up(stride, 128), 128, 0, st, (const uint4*)c_w, (const uint4*)pw_w, stride, c_w);
     }
     const size_t wlen = std::min(stride, key_len);
-    PB_TRY(msm_run(P->srs, 0, (const uint64_t*)agg, wlen, 2, stride, aff, st));
+    PB_TRY(msm_run(P->srs, 0, (const uint64_t*)agg, wlen, 2, stride, aff, st, ar));
     compress_affine(aff, c48[9]);
     compress_affine(aff + 12, c48[10]);
   }
