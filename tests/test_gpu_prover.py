@@ -115,3 +115,63 @@ def test_gpu_prover_2_18_gates_matches_cpu_oracle(pb):
     assert gpu.commitments() == cpu.commitments()
     blinders = cref.draw_blinders(R.StdRng.seed_from_u64(18))
     assert gpu.prove(arrays.witnesses, arrays.pi_idx, arrays.pi_vals, blinders) == cpu.prove(blinders)
+
+
+def test_gpu_prover_concurrent_threads_are_deterministic(pb):
+    """The C ABI is called concurrently from several host threads (as rayon workers would): every
+    thread must get the same bytes as a lone call."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    rng = random.Random(4)
+    srs_raw = cref.srs_from_secret((1 << 11) + 7, rng.randrange(1, R.R_MOD), rng.randrange(1, R.R_MOD))
+    comp = R.Composer.initialized()
+    R.synthetic_arith_circuit(comp, (1 << 10) - 6, seed=41, widgets=4)
+    arrays = cref.CircuitArrays(comp)
+    gpu = _gpu_prover(pb, b"threads", arrays, srs_raw)
+    blinders = [cref.draw_blinders(R.StdRng.seed_from_u64(s)) for s in range(6)]
+    alone = [gpu.prove(arrays.witnesses, arrays.pi_idx, arrays.pi_vals, b) for b in blinders]
+    with ThreadPoolExecutor(6) as ex:
+        for _ in range(3):
+            got = list(ex.map(lambda b: gpu.prove(arrays.witnesses, arrays.pi_idx, arrays.pi_vals, b), blinders))
+            assert got == alone
+    assert len(set(alone)) == 6  # different blinders, different proofs
+
+
+def test_gpu_prover_rejects_bad_arguments(pb):
+    rng = random.Random(5)
+    srs_raw = cref.srs_from_secret(64 + 7, rng.randrange(1, R.R_MOD), rng.randrange(1, R.R_MOD))
+    comp = R.Composer.initialized()
+    R.synthetic_arith_circuit(comp, 58, seed=5)
+    arrays = cref.CircuitArrays(comp)
+    with pytest.raises(pb.Pb200Error):  # commit key too small for the circuit (TruncatedDegreeTooLarge)
+        pb.Prover(b"x", arrays.constraints, arrays.selectors, arrays.wires, arrays.n_witnesses, srs_raw[: 96 * 40])
+    gpu = _gpu_prover(pb, b"x", arrays, srs_raw)
+    from plonk_b200._lib import lib
+    import ctypes
+
+    out = ctypes.create_string_buffer(1008)
+    bl = cref.draw_blinders(R.StdRng.seed_from_u64(1))
+    # wrong witness count
+    assert lib().pb200_prove(gpu._h, arrays.witnesses, arrays.n_witnesses - 1, arrays.pi_idx, arrays.pi_vals, arrays.n_pi, bl, out) == -4
+    # public input position outside the circuit
+    bad_idx = (10**6).to_bytes(8, "little") + arrays.pi_idx[8:]
+    assert lib().pb200_prove(gpu._h, arrays.witnesses, arrays.n_witnesses, bad_idx, arrays.pi_vals, arrays.n_pi, bl, out) == -4
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("PB200_SLOW"), reason="several minutes; set PB200_SLOW=1")
+def test_gpu_prover_2_20_gates_matches_cpu_oracle(pb):
+    """BASELINE.json configs[2]: 2^20-gate circuit (quotient domain 2^23, 2^20-point commit key)."""
+    from plonk_b200._lib import check, lib
+    from plonk_b200.composer import synthetic_circuit
+    import ctypes
+
+    log_gates = 20
+    n_srs = (1 << log_gates) + 7
+    raw = ctypes.create_string_buffer(96 * n_srs)
+    check(lib().pb200_srs_setup_from_secret(R.fr_to_mont_bytes(0xABCDEF), R.fr_to_mont_bytes(0x13579), n_srs, raw))
+    arrays = synthetic_circuit((1 << log_gates) - 6, seed=20, widgets=2).arrays()
+    cpu = cref.CrefProver(b"bench-2^20", arrays, raw.raw)
+    gpu = _gpu_prover(pb, b"bench-2^20", arrays, raw.raw)
+    assert gpu.commitments() == cpu.commitments()
+    blinders = cref.draw_blinders(R.StdRng.seed_from_u64(20))
+    assert gpu.prove(arrays.witnesses, arrays.pi_idx, arrays.pi_vals, blinders) == cpu.prove(blinders)
