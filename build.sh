@@ -14,5 +14,5 @@ for f in capi ntt msm prover; do
 done
 g++ -std=c++17 -O2 -fPIC -c -o $OBJ/host_field.o $SRC/host_field.cpp
 for p in "${pids[@]}"; do wait $p; done
-nvcc -shared -o "$OUT" $OBJ/capi.o $OBJ/ntt.o $OBJ/msm.o $OBJ/prover.o $OBJ/host_field.o -lcudart
+nvcc -shared -o "$OUT" $OBJ/capi.o $OBJ/ntt.o $OBJ/msm.o $OBJ/prover.o $OBJ/host_field.o
 echo "built $OUT"

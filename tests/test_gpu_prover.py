@@ -175,3 +175,26 @@ def test_gpu_prover_2_20_gates_matches_cpu_oracle(pb):
     assert gpu.commitments() == cpu.commitments()
     blinders = cref.draw_blinders(R.StdRng.seed_from_u64(20))
     assert gpu.prove(arrays.witnesses, arrays.pi_idx, arrays.pi_vals, blinders) == cpu.prove(blinders)
+
+
+def test_cpp_mirror_produces_the_same_proof(pb, tmp_path):
+    """include/plonk_b200.hpp (EvaluationDomain / CommitKey / Prover in C++) end to end."""
+    import struct
+    import subprocess
+
+    from tests.test_host_logic import _build_api_check
+
+    rng = random.Random(6)
+    srs_raw = cref.srs_from_secret(256 + 7, rng.randrange(1, R.R_MOD), rng.randrange(1, R.R_MOD))
+    comp = R.Composer.initialized()
+    R.synthetic_arith_circuit(comp, 250, seed=61, n_public=2, widgets=5)
+    a = cref.CircuitArrays(comp)
+    bl = cref.draw_blinders(R.StdRng.seed_from_u64(6))
+    label = b"cpp-mirror"
+    blob = struct.pack("<5Q", len(srs_raw) // 96, a.constraints, a.n_witnesses, a.n_pi, len(label))
+    blob += srs_raw + a.selectors + a.wires + a.witnesses + a.pi_idx + a.pi_vals + bl + label
+    f = tmp_path / "case.bin"
+    f.write_bytes(blob)
+    out = subprocess.run([_build_api_check(), str(f)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.strip() == cref.CrefProver(label, a, srs_raw).prove(bl).hex()

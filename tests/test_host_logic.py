@@ -59,3 +59,20 @@ def test_no_cuda_device_fails_loudly():
 
     out = ctypes.create_string_buffer(64)
     assert lib().pb200_ntt(bytes(64), 2, out, 1, 0, 0, 1, 2, 2) == -1
+
+
+def _build_api_check():
+    import subprocess
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    exe = os.path.join(here, "cpp", "api_check")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(here, "cpp", "api_check.cpp"),
+                           "-L" + os.path.join(root, "plonk_b200"), "-lplonk_b200",
+                           "-Wl,-rpath," + os.path.join(root, "plonk_b200")])
+    return exe
+
+
+def test_cpp_mirror_header_compiles_and_links():
+    """include/plonk_b200.hpp (the compiled-language mirror of the reference interface) against the .so."""
+    assert os.path.exists(_build_api_check())
