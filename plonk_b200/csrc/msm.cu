@@ -38,7 +38,7 @@ struct pb200_srs {
 namespace pb {
 
 static constexpr int kGroup = 8;
-static constexpr unsigned kHeavy = 512;  // buckets longer than this get a whole CTA (skewed scalar distributions)  // buckets per running-sum group in the reduction
+static constexpr unsigned kHeavy = 512;  // buckets longer than this many size units (~8x the average) get a whole CTA  // buckets per running-sum group in the reduction
 
 PB_D G1Affine ld_affine(const uint4* p, size_t i) {
   const uint4* q = p + 6 * i;
@@ -175,7 +175,7 @@ __global__ void k_msm_digits(const uint4* scalars, size_t n, size_t stride, int 
 // clipped size), so that the threads of a warp in k_msm_accumulate get buckets of near-equal length
 // and the warp does not idle on its longest lane.
 __global__ void __launch_bounds__(1024) k_msm_scan(const unsigned* counts, unsigned* offsets, unsigned* order, unsigned* n_heavy,
-                                                   unsigned nb) {
+                                                   unsigned nb, int size_shift) {
   __shared__ unsigned sums[1024];
   __shared__ unsigned bins[1024];
   const unsigned b = blockIdx.x, tid = threadIdx.x;
@@ -201,8 +201,9 @@ __global__ void __launch_bounds__(1024) k_msm_scan(const unsigned* counts, unsig
     run += cnt[k];
   }
   if (tid == 1023) off[nb] = sums[1023];
-  // counting sort of the buckets by size, largest first (bin 0 = size >= 1023)
-  for (unsigned k = tid; k < nb; k += 1024) atomicAdd(&bins[1023u - min(cnt[k], 1023u)], 1u);
+  // counting sort of the buckets by size (in units of 2^size_shift entries, so that the average
+  // bucket lands near bin 64 whatever the MSM size), largest first (bin 0 = size >= 1023 units)
+  for (unsigned k = tid; k < nb; k += 1024) atomicAdd(&bins[1023u - min(cnt[k] >> size_shift, 1023u)], 1u);
   __syncthreads();
   const unsigned mine = bins[tid];
   sums[tid] = mine;
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(1024) k_msm_scan(const unsigned* counts, unsig
   if (tid == 1022u - kHeavy) n_heavy[b] = sums[tid];  // bins 0 .. 1022-kHeavy hold the sizes > kHeavy
   __syncthreads();
   for (unsigned k = tid; k < nb; k += 1024) {
-    const unsigned pos = atomicAdd(&bins[1023u - min(cnt[k], 1023u)], 1u);
+    const unsigned pos = atomicAdd(&bins[1023u - min(cnt[k] >> size_shift, 1023u)], 1u);
     ord[pos] = k;
   }
 }
@@ -385,12 +386,12 @@ PB_D G1Xyzz warp_sum(G1Xyzz v) {
   return v;
 }
 
-// One warp per class; 4 warps per CTA.  out is [batch][nclasses].
+// One warp per (class, chunk of 512 members); 4 warps per CTA.  out is [batch][nclasses][chunks].
 __global__ void __launch_bounds__(128) k_msm_group_classes(const uint4* S, const uint4* A, unsigned n_groups,
-                                                           DigitPlan plan, uint4* out) {
+                                                           DigitPlan plan, unsigned chunks, uint4* out) {
   const int cls = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  const unsigned b = blockIdx.y;
+  const unsigned b = blockIdx.y, chunk = blockIdx.z;
   if (cls >= plan.nclasses) return;
   G1Xyzz acc = G1Xyzz::identity();
   if (cls < plan.n_digit_classes) {
@@ -399,12 +400,12 @@ __global__ void __launch_bounds__(128) k_msm_group_classes(const uint4* S, const
     const unsigned v = cls - plan.first_class[j];
     const int sh_j = plan.shift[j], bits_j = plan.bits[j];
     const unsigned count = n_groups >> bits_j;
-    for (unsigned idx = lane; idx < count; idx += 32) {
+    for (unsigned idx = chunk * 512u + lane; idx < min(count, (chunk + 1) * 512u); idx += 32) {
       const unsigned G = ((idx >> sh_j) << (sh_j + bits_j)) | (v << sh_j) | (idx & ((1u << sh_j) - 1u));
       G1Xyzz q = ld_xyzz(S, (size_t)b * n_groups + G);
       xyzz_add(acc, q);
     }
-  } else {
+  } else if (chunk == 0) {
     const unsigned first = (unsigned)(cls - plan.n_digit_classes) * 256u;
     for (unsigned G = first + lane; G < min(n_groups, first + 256u); G += 32) {
       G1Xyzz q = ld_xyzz(A, (size_t)b * n_groups + G);
@@ -412,16 +413,21 @@ __global__ void __launch_bounds__(128) k_msm_group_classes(const uint4* S, const
     }
   }
   acc = warp_sum(acc);
-  if (lane == 0) st_xyzz(out, (size_t)b * plan.nclasses + cls, acc);
+  if (lane == 0) st_xyzz(out, ((size_t)b * plan.nclasses + cls) * chunks + chunk, acc);
 }
 
 // out is [batch][ndig + 1]: D_0 .. D_{ndig-1}, then the sum of all A_G.
-__global__ void __launch_bounds__(256) k_msm_final(const uint4* classes, DigitPlan plan, uint4* out) {
+__global__ void __launch_bounds__(256) k_msm_final(const uint4* classes, DigitPlan plan, unsigned chunks, uint4* out) {
   const int lane = threadIdx.x & 31, j = threadIdx.x >> 5;
   const unsigned b = blockIdx.x;
   if (j < plan.ndig) {
     const int nv = 1 << plan.bits[j];
-    G1Xyzz x = (lane < nv) ? ld_xyzz(classes, (size_t)b * plan.nclasses + plan.first_class[j] + lane) : G1Xyzz::identity();
+    G1Xyzz x = G1Xyzz::identity();
+    if (lane < nv)
+      for (unsigned ch = 0; ch < chunks; ch++) {
+        G1Xyzz q = ld_xyzz(classes, ((size_t)b * plan.nclasses + plan.first_class[j] + lane) * chunks + ch);
+        xyzz_add(x, q);
+      }
     for (int d = 1; d < nv; d <<= 1) {  // inclusive suffix scan over lanes 0..nv-1
       G1Xyzz o = shfl_down_xyzz(x, d, 32);
       if (lane + d < nv) xyzz_add(x, o);
@@ -435,7 +441,7 @@ __global__ void __launch_bounds__(256) k_msm_final(const uint4* classes, DigitPl
   } else if (j == 7) {
     G1Xyzz acc = G1Xyzz::identity();
     for (int k = lane; k < plan.n_a_classes; k += 32) {
-      G1Xyzz q = ld_xyzz(classes, (size_t)b * plan.nclasses + plan.n_digit_classes + k);
+      G1Xyzz q = ld_xyzz(classes, ((size_t)b * plan.nclasses + plan.n_digit_classes + k) * chunks);
       xyzz_add(acc, q);
     }
     acc = warp_sum(acc);
@@ -492,11 +498,11 @@ std::atomic<uint64_t> g_prof_acc_ns{0}, g_prof_acc_adds{0}, g_prof_acc_launches{
 static int pick_window(size_t n_points) {
   if (const char* env = getenv("PB200_MSM_C")) {
     int c = atoi(env);
-    if (c >= 2 && c <= 16) return c;
+    if (c >= 2 && c <= 20) return c;
   }
   int lg = 0;
   while (((size_t)1 << (lg + 1)) <= n_points) lg++;
-  return std::min(16, std::max(4, lg));
+  return std::min(20, std::max(4, lg));
 }
 
 static void xyzz_dev_to_host(const uint32_t* w, pbh::HXyzz* o) {
@@ -562,7 +568,9 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
   PB_ALLOC(epos, (size_t)batch * cap * 4, st, ar);
   PB_ALLOC(sorted, (size_t)batch * cap * 4, st, ar);
   PB_ALLOC(sums, (size_t)batch * nb * 192, st, ar);
-  PB_ALLOC(classes, (size_t)batch * plan.nclasses * 192, st, ar);
+  unsigned chunks = 1;
+  for (int j = 0; j < plan.ndig; j++) chunks = std::max<unsigned>(chunks, (unsigned)(((n_groups >> plan.bits[j]) + 511) / 512));
+  PB_ALLOC(classes, (size_t)batch * plan.nclasses * chunks * 192, st, ar);
   PB_ALLOC(S, (size_t)batch * n_groups * 192, st, ar);
   PB_ALLOC(A, (size_t)batch * n_groups * 192, st, ar);
   PB_ALLOC(result, (size_t)batch * (plan.ndig + 1) * 192, st, ar);
@@ -570,7 +578,9 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
 
   PB_LAUNCH(k_msm_digits, dim3(div_up(n, 128), batch), 128, 0, st, (const uint4*)d_scalars, n, stride, c, W, nb,
             counts, ebkt, epos);
-  PB_LAUNCH(k_msm_scan, batch, 1024, 0, st, counts, offsets, order, n_heavy, nb);
+  int size_shift = 0;  // size unit: average bucket ~ 64 units
+  while (((cap / nb) >> size_shift) > 64) size_shift++;
+  PB_LAUNCH(k_msm_scan, batch, 1024, 0, st, counts, offsets, order, n_heavy, nb, size_shift);
   PB_LAUNCH(k_msm_scatter, dim3(div_up(n, 256), W, batch), 256, 0, st, ebkt, epos, offsets, n, W, nb,
             srs->n_points, first, sorted);
   const bool prof = g_prof_on.load(std::memory_order_relaxed) != 0;
@@ -600,9 +610,9 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
   }
   PB_LAUNCH(k_msm_accumulate_heavy, dim3(64, batch), 128, 0, st, srs->table, sorted, offsets, order, n_heavy, nb, cap, sums);
   PB_LAUNCH(k_msm_groups, dim3(div_up(n_groups, 64), batch), 64, 0, st, (const uint4*)sums, nb, g, S, A);
-  PB_LAUNCH(k_msm_group_classes, dim3(div_up(plan.nclasses, 4), batch), 128, 0, st, (const uint4*)S, (const uint4*)A, n_groups,
-            plan, classes);
-  PB_LAUNCH(k_msm_final, batch, 256, 0, st, (const uint4*)classes, plan, result);
+  PB_LAUNCH(k_msm_group_classes, dim3(div_up(plan.nclasses, 4), batch, chunks), 128, 0, st, (const uint4*)S, (const uint4*)A,
+            n_groups, plan, chunks, classes);
+  PB_LAUNCH(k_msm_final, batch, 256, 0, st, (const uint4*)classes, plan, chunks, result);
   PB_CUDA(cudaGetLastError());
   std::vector<uint32_t> host((size_t)batch * (plan.ndig + 1) * 48);
   PB_CUDA(cudaMemcpyAsync(host.data(), result, host.size() * 4, cudaMemcpyDeviceToHost, st));
@@ -679,7 +689,7 @@ size_t msm_workspace_bytes(const pb200_srs* srs, size_t n, uint32_t batch) {
   b += 3 * ((size_t)batch * cap * 4 + 256);            // ebkt, epos, sorted
   b += (size_t)batch * nb * 192 + 256;                 // sums
   b += 2 * ((size_t)batch * n_groups * 192 + 256);     // S, A
-  b += (size_t)batch * (8 * 16 + n_groups / 256 + 2) * 192 + 256;  // classes
+  b += (size_t)batch * (8 * 16 + n_groups / 256 + 2) * (n_groups / 8192 + 1) * 192 + 256;  // classes x chunks
   b += (size_t)batch * 9 * 192 + 256;                  // result
   return b + 4096;
 }
