@@ -279,66 +279,9 @@ struct Field {
   }
   PB_HD Field sqr() const { return (*this) * (*this); }
 
-  // K independent Montgomery products with their rows interleaved in program order.  One product is
-  // a chain of ~13 dependent IMAD.WIDE per row (carry-linked), so a lone thread leaves the integer
-  // pipe mostly idle; interleaving K products gives the scheduler K independent chains.  Used by the
-  // group-law formulas, whose multiplications come in independent batches.
-  template <int K>
-  static PB_HD void mul_many(Field* out, const Field* a, const Field* b) {
-    uint32_t A[K][N], B[K][N];
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-      const uint32_t bi = b[k].v[0];
-#pragma unroll
-      for (int j = 0; j < N; j += 2) {
-        mul_pair(A[k][j], A[k][j + 1], a[k].v[j], bi);
-        mul_pair(B[k][j], B[k][j + 1], a[k].v[j + 1], bi);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < K; k++) mont_row<true>(B[k], A[k], a[k].v, b[k].v[0]);
-#pragma unroll
-    for (int i = 1; i < N; i += 2) {
-#pragma unroll
-      for (int k = 0; k < K; k++) mont_row<false>(A[k], B[k], a[k].v, b[k].v[i]);
-      if (i + 1 < N) {
-#pragma unroll
-        for (int k = 0; k < K; k++) mont_row<false>(B[k], A[k], a[k].v, b[k].v[i + 1]);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-      uint32_t t[N];
-      t[0] = add_cc(A[k][0], B[k][1]);
-#pragma unroll
-      for (int j = 1; j < N - 1; j++) t[j] = addc_cc(A[k][j], B[k][j + 1]);
-      t[N - 1] = addc(A[k][N - 1], 0u);
-      final_sub(out[k].v, t, 0u);
-    }
-  }
-  static PB_HD void mul2(Field& r0, const Field& a0, const Field& b0, Field& r1, const Field& a1, const Field& b1) {
-    Field a[2] = {a0, a1}, b[2] = {b0, b1}, o[2];
-    mul_many<2>(o, a, b);
-    r0 = o[0];
-    r1 = o[1];
-  }
-  static PB_HD void mul3(Field& r0, const Field& a0, const Field& b0, Field& r1, const Field& a1, const Field& b1,
-                         Field& r2, const Field& a2, const Field& b2) {
-    Field a[3] = {a0, a1, a2}, b[3] = {b0, b1, b2}, o[3];
-    mul_many<3>(o, a, b);
-    r0 = o[0];
-    r1 = o[1];
-    r2 = o[2];
-  }
-  static PB_HD void mul4(Field& r0, const Field& a0, const Field& b0, Field& r1, const Field& a1, const Field& b1,
-                         Field& r2, const Field& a2, const Field& b2, Field& r3, const Field& a3, const Field& b3) {
-    Field a[4] = {a0, a1, a2, a3}, b[4] = {b0, b1, b2, b3}, o[4];
-    mul_many<4>(o, a, b);
-    r0 = o[0];
-    r1 = o[1];
-    r2 = o[2];
-    r3 = o[3];
-  }
+  // (Interleaving several independent products in program order was tried for instruction-level
+  // parallelism and gives nothing: ptxas keeps at most ~6 carry chains in flight - there are only 7
+  // predicate registers - and one product already uses 4.  See DESIGN.md section 4.)
 
   // out of / into Montgomery form
   PB_HD Field from_mont() const {

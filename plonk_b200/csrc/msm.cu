@@ -502,7 +502,11 @@ static int pick_window(size_t n_points) {
   }
   int lg = 0;
   while (((size_t)1 << (lg + 1)) <= n_points) lg++;
-  return std::min(20, std::max(4, lg));
+  // up to 2^16 points: c = log2(n) (~32 entries per bucket with W = 256/c windows); larger keys keep
+  // ~100+ entries per bucket so that the latency-bound bucket reduction stays small next to the
+  // accumulation (measured on the 2^16..2^22 sweep, tools/msm_sweep.py)
+  if (lg <= 16) return std::max(4, lg);
+  return std::min(20, std::max(16, lg - 2));
 }
 
 static void xyzz_dev_to_host(const uint32_t* w, pbh::HXyzz* o) {
