@@ -502,11 +502,11 @@ static int pick_window(size_t n_points) {
   }
   int lg = 0;
   while (((size_t)1 << (lg + 1)) <= n_points) lg++;
-  // up to 2^16 points: c = log2(n) (~32 entries per bucket with W = 256/c windows); larger keys keep
-  // ~100+ entries per bucket so that the latency-bound bucket reduction stays small next to the
-  // accumulation (measured on the 2^16..2^22 sweep, tools/msm_sweep.py)
+  // up to 2^16 points: c = log2(n) (~32 entries per bucket with W = 256/c windows).  Above that the
+  // choice follows the measured sweep (tools/msm_sweep.py, one B200): 2^18 points 3.1 ms at c = 16 vs
+  // 6.2 ms at c = 18; 2^20 points 7.9 ms at c = 20 vs 20 ms at c = 18 and 61 ms at c = 16.
   if (lg <= 16) return std::max(4, lg);
-  return std::min(20, std::max(16, lg - 2));
+  return lg <= 19 ? 16 : 20;
 }
 
 static void xyzz_dev_to_host(const uint32_t* w, pbh::HXyzz* o) {
