@@ -2,8 +2,8 @@
 the GPUs of a box; per-rank partial results are all-gathered over NCCL and added locally
 (plonk_b200/dist.py).
 
-  python tools/msm_sweep.py --logs 16,18,20                       # one GPU
-  python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/msm_sweep.py --logs 16,20,22,24
+  python tools/msm_sweep.py --sizes 16,18,20                       # one GPU
+  python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/msm_sweep.py --sizes 16,20,22,24
 
 Every rank generates the same seeded commit key on its own GPU ([x^i] g, pb200_srs_setup_from_secret),
 uploads only its slice, and checks the reduced result against [p(x)] g computed by rank 0 on the GPU
@@ -28,7 +28,7 @@ mont = lambda v: ((v << 256) % R_MOD).to_bytes(32, "little")
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--logs", default="16,18,20")
+    ap.add_argument("--sizes", default="16,18,20")
     ap.add_argument("--iters", type=int, default=3)
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
@@ -38,7 +38,7 @@ def main():
     L = lib()
     check(L.pb200_init(local))
     x, gs = 0x1234567, 0x7654321
-    for log_n in (int(v) for v in args.logs.split(",")):
+    for log_n in (int(v) for v in args.sizes.split(",")):
         n = 1 << log_n
         first, count = pd.shard_range(n, rank, world)
         # this rank's slice of the key: [x^(first+i)] g = [x^i] ([x^first] g)
