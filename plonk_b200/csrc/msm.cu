@@ -37,7 +37,8 @@ struct pb200_srs {
 
 namespace pb {
 
-static constexpr int kGroup = 8;
+static constexpr int kGroup = 4;
+static constexpr unsigned kClassChunk = 256;  // members of a class summed by one warp
 static constexpr unsigned kHeavy = 512;  // buckets longer than this many size units (~8x the average) get a whole CTA  // buckets per running-sum group in the reduction
 
 PB_D G1Affine ld_affine(const uint4* p, size_t i) {
@@ -252,8 +253,8 @@ PB_D G1Xyzz shfl_down_xyzz(const G1Xyzz& p, int delta, int width) {
 // Bucket accumulation: thread = (bucket, part); the 2^log_split parts of a bucket are adjacent
 // lanes and are merged with a warp-shuffle tree, so `sums` holds one XYZZ point per bucket
 // ([batch][nb]).  Buckets are visited in `order` (largest first, near-equal sizes per warp).
-template <int MIN_CTAS>
-__global__ void __launch_bounds__(128, MIN_CTAS) k_msm_accumulate(const uint4* table, const unsigned* sorted,
+template <int THREADS, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS) k_msm_accumulate(const uint4* table, const unsigned* sorted,
                                                                const unsigned* offsets, const unsigned* order,
                                                                const unsigned* n_heavy, unsigned nb, int log_split, size_t cap,
                                                                uint4* sums) {
@@ -344,8 +345,8 @@ __global__ void __launch_bounds__(128) k_msm_accumulate_heavy(const uint4* table
 // Bucket reduction  R = sum_b (b + 1) B_b.  A single GPU thread needs ~15 us per dependent group
 // addition (14 carry-chained Fp products), so the reduction is organised to be work-efficient first
 // (it shares the SMs with other proofs' accumulation kernels) and shallow second:
-//   A. k_msm_groups: one thread per group of g = 8 consecutive buckets, running sums:
-//        S_G = sum_j B[8G + j],  A_G = sum_j (j + 1) B[8G + j]          => R = sum A_G + 8 sum G S_G
+//   A. k_msm_groups: one thread per group of g = kGroup consecutive buckets, running sums:
+//        S_G = sum_j B[gG + j],  A_G = sum_j (j + 1) B[gG + j]          => R = sum A_G + g sum G S_G
 //   B. k_msm_group_classes: the group index G is cut into digits of <= 4 bits; class (j, v) is the
 //      plain sum of S_G over the groups whose digit j equals v; further classes hold partial plain
 //      sums of A_G.  One warp per class: 8..16 serial additions per lane + a 5-level shuffle tree.
@@ -386,7 +387,7 @@ PB_D G1Xyzz warp_sum(G1Xyzz v) {
   return v;
 }
 
-// One warp per (class, chunk of 512 members); 4 warps per CTA.  out is [batch][nclasses][chunks].
+// One warp per (class, chunk of kClassChunk members); 4 warps per CTA.  out is [batch][nclasses][chunks].
 __global__ void __launch_bounds__(128) k_msm_group_classes(const uint4* S, const uint4* A, unsigned n_groups,
                                                            DigitPlan plan, unsigned chunks, uint4* out) {
   const int cls = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -400,7 +401,7 @@ __global__ void __launch_bounds__(128) k_msm_group_classes(const uint4* S, const
     const unsigned v = cls - plan.first_class[j];
     const int sh_j = plan.shift[j], bits_j = plan.bits[j];
     const unsigned count = n_groups >> bits_j;
-    for (unsigned idx = chunk * 512u + lane; idx < min(count, (chunk + 1) * 512u); idx += 32) {
+    for (unsigned idx = chunk * kClassChunk + lane; idx < min(count, (chunk + 1) * kClassChunk); idx += 32) {
       const unsigned G = ((idx >> sh_j) << (sh_j + bits_j)) | (v << sh_j) | (idx & ((1u << sh_j) - 1u));
       G1Xyzz q = ld_xyzz(S, (size_t)b * n_groups + G);
       xyzz_add(acc, q);
@@ -573,7 +574,7 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
   PB_ALLOC(sorted, (size_t)batch * cap * 4, st, ar);
   PB_ALLOC(sums, (size_t)batch * nb * 192, st, ar);
   unsigned chunks = 1;
-  for (int j = 0; j < plan.ndig; j++) chunks = std::max<unsigned>(chunks, (unsigned)(((n_groups >> plan.bits[j]) + 511) / 512));
+  for (int j = 0; j < plan.ndig; j++) chunks = std::max<unsigned>(chunks, (unsigned)(((n_groups >> plan.bits[j]) + kClassChunk - 1) / kClassChunk));
   PB_ALLOC(classes, (size_t)batch * plan.nclasses * chunks * 192, st, ar);
   PB_ALLOC(S, (size_t)batch * n_groups * 192, st, ar);
   PB_ALLOC(A, (size_t)batch * n_groups * 192, st, ar);
@@ -595,17 +596,19 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
     PB_CUDA(cudaEventRecord(ev0, st));
   }
   {
-    static const int min_ctas = [] {
-      const char* e = getenv("PB200_ACC_MIN_CTAS");
-      return e ? atoi(e) : 2;
+    // CTA shape: 64 threads x 4 CTAs/SM and 128 x 2 hold the same 8 warps per SM (register-limited);
+    // the smaller CTA balances the tail of the launch better when there are few waves.
+    static const int acc_block = [] {
+      const char* e = getenv("PB200_ACC_BLOCK");
+      return e ? atoi(e) : 64;
     }();
-    const dim3 grid(div_up((size_t)nb << log_split, 128), batch);
-    if (min_ctas >= 4)
-      PB_LAUNCH(k_msm_accumulate<4>, grid, 128, 0, st, srs->table, sorted, offsets, order, n_heavy, nb, log_split, cap, sums);
-    else if (min_ctas == 3)
-      PB_LAUNCH(k_msm_accumulate<3>, grid, 128, 0, st, srs->table, sorted, offsets, order, n_heavy, nb, log_split, cap, sums);
-    else
-      PB_LAUNCH(k_msm_accumulate<2>, grid, 128, 0, st, srs->table, sorted, offsets, order, n_heavy, nb, log_split, cap, sums);
+    if (acc_block == 64) {
+      const dim3 grid(div_up((size_t)nb << log_split, 64), batch);
+      PB_LAUNCH((k_msm_accumulate<64, 4>), grid, 64, 0, st, srs->table, sorted, offsets, order, n_heavy, nb, log_split, cap, sums);
+    } else {
+      const dim3 grid(div_up((size_t)nb << log_split, 128), batch);
+      PB_LAUNCH((k_msm_accumulate<128, 2>), grid, 128, 0, st, srs->table, sorted, offsets, order, n_heavy, nb, log_split, cap, sums);
+    }
   }
   std::vector<unsigned> h_tot(batch, 0);
   if (prof) {
@@ -693,7 +696,7 @@ size_t msm_workspace_bytes(const pb200_srs* srs, size_t n, uint32_t batch) {
   b += 3 * ((size_t)batch * cap * 4 + 256);            // ebkt, epos, sorted
   b += (size_t)batch * nb * 192 + 256;                 // sums
   b += 2 * ((size_t)batch * n_groups * 192 + 256);     // S, A
-  b += (size_t)batch * (8 * 16 + n_groups / 256 + 2) * (n_groups / 8192 + 1) * 192 + 256;  // classes x chunks
+  b += (size_t)batch * (8 * 16 + n_groups / 256 + 2) * (n_groups / (16 * kClassChunk) + 2) * 192 + 256;  // classes x chunks
   b += (size_t)batch * 9 * 192 + 256;                  // result
   return b + 4096;
 }
