@@ -600,7 +600,7 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
     // the smaller CTA balances the tail of the launch better when there are few waves.
     static const int acc_block = [] {
       const char* e = getenv("PB200_ACC_BLOCK");
-      return e ? atoi(e) : 64;
+      return e ? atoi(e) : 128;
     }();
     if (acc_block == 64) {
       const dim3 grid(div_up((size_t)nb << log_split, 64), batch);
