@@ -212,6 +212,9 @@ def run_ours(args):
         "single_stream_ms_per_proof": single_ms,
         "alu": {"unit": "G1 adds/s", "achieved": adds_per_s, "peak": imad.value / IMAD_PER_ADD,
                 "frac": adds_per_s / (imad.value / IMAD_PER_ADD), "imad_wide_per_s_measured": imad.value,
+                "carry_chain_ceiling": {"fp_products_per_s": 30.3e9, "adds_per_s": 3.03e9, "frac": adds_per_s / 3.03e9,
+                                        "source": "tools/mulbench on this pool's B200: IMAD.WIDE.U32.X (carry in/out) issues at half the "
+                                                  "rate of carry-free IMAD.WIDE; 10 Fp products per mixed addition"},
                 "note": "both hot kernels are IMAD-pipe bound at 256/381-bit precision; HBM fraction is reported because the contract asks for it"},
     }
     ntt = ntt_microbench(L, torch, imad.value)
