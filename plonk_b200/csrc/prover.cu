@@ -624,8 +624,8 @@ int prover_new(const uint8_t* label, size_t label_len, size_t constraints, const
   cudaFreeAsync(cols, st);
   {  // arena size for one proof: prover scratch + the larger of (NTT scratch, MSM scratch)
     const size_t stride = n + 8;
-    const size_t elems = 8 * n + 15 * stride + 64 * n + 64 + 16 * (size_t)div_up(stride, 2048) + 4 * (size_t)div_up(stride, 2048);
-    const size_t ntt_tmp = 5 * n8 * 32;
+    const size_t elems = 8 * n + 16 * stride + 64 * n + 64 + 16 * (size_t)div_up(stride, 2048) + 4 * (size_t)div_up(stride, 2048);
+    const size_t ntt_tmp = 6 * n8 * 32;
     const size_t msm_ws = msm_workspace_bytes(P->srs, std::min(stride, srs_len(P->srs)), 4);
     P->ws_bytes = elems * 32 + std::max(ntt_tmp, msm_ws) + (size_t)64 * 256 + (1 << 20);
   }
@@ -700,8 +700,8 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
   uint4 *wv, *wp, *zp, *num, *den, *w8, *quot, *tcoef, *tq, *pi_dense, *agg, *pw, *scratch, *evals_d, *partial;
   unsigned* flag;
   const unsigned eval_blocks = div_up(stride, 2048);
-  PB_ALLOC(wv, 4 * n * 32, st, ar);
-  PB_ALLOC(zp, 5 * stride * 32, st, ar);  // [z, a, b, c, d], one coset-NTT batch in round 3
+  PB_ALLOC(wv, 5 * n * 32, st, ar);       // wire values a, b, c, d and the dense public-input vector
+  PB_ALLOC(zp, 6 * stride * 32, st, ar);  // [z, a, b, c, d, pi] coefficient form: one coset-NTT batch in round 3
   wp = zp + 2 * stride;
   PB_ALLOC(num, n * 32, st, ar);
   PB_ALLOC(den, n * 32, st, ar);
@@ -709,7 +709,7 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
   PB_ALLOC(quot, n8 * 32, st, ar);
   PB_ALLOC(tcoef, n8 * 32, st, ar);
   PB_ALLOC(tq, 4 * stride * 32, st, ar);
-  PB_ALLOC(pi_dense, 2 * n * 32, st, ar);
+  pi_dense = wv + 2 * 4 * n;
   PB_ALLOC(agg, 2 * stride * 32, st, ar);
   PB_ALLOC(pw, 2 * stride * 32, st, ar);
   PB_ALLOC(scratch, 2 * stride * 32, st, ar);
@@ -722,8 +722,14 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
 
   // ---- round 1 -------------------------------------------------------------------------------
   PB_LAUNCH(k_gather_wires, dim3(div_up(n, 256), 4), 256, 0, st, (const uint4*)d_wit, (const uint32_t*)P->d_wires, P->constraints, n, wv);
-  PB_CUDA(cudaMemsetAsync(wp, 0, 4 * stride * 32, st));
-  PB_TRY(ntt_run((const uint64_t*)wv, n, (uint64_t*)wp, log_n, 1, 0, 4, n, stride, st, ar));
+  // dense public-input vector (prover.rs:434-438) rides along with the wire iNTTs (prover.rs:519-521)
+  if (n_pi) {
+    PB_CUDA(cudaMemsetAsync(pi_dense, 0, n * 32, st));
+    for (size_t i = 0; i < n_pi; i++)
+      PB_CUDA(cudaMemcpyAsync(pi_dense + 2 * pi_idx[i], PIV + i, 32, cudaMemcpyHostToDevice, st));
+  }
+  PB_CUDA(cudaMemsetAsync(zp, 0, 6 * stride * 32, st));
+  PB_TRY(ntt_run((const uint64_t*)wv, n, (uint64_t*)wp, log_n, 1, 0, n_pi ? 5 : 4, n, stride, st, ar));
   {
     BlindArgs ba;
     ba.nb = 2;
@@ -746,7 +752,6 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
   PB_LAUNCH(k_perm_terms, div_up(n, 128), 128, 0, st, (const uint4*)wv, (const uint4*)P->d_sigma, w_half, n, to_dev(beta), to_dev(gamma), num, den);
   PB_LAUNCH(k_batch_div, div_up(div_up(n, 8), 128), 128, 0, st, (const uint4*)num, (const uint4*)den, n, num);
   PB_TRY((fr_scan<true, false>(num, n, den, st, ar)));  // den <- permutation vector z[i] = prod_{j<i} num_j/den_j
-  PB_CUDA(cudaMemsetAsync(zp, 0, stride * 32, st));
   PB_TRY(ntt_run((const uint64_t*)den, n, (uint64_t*)zp, log_n, 1, 0, 1, n, stride, st, ar));
   {
     BlindArgs ba;
@@ -765,17 +770,10 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
   const HFr ch_logic = tr.challenge_scalar("logic separation challenge");
   const HFr ch_fixed = tr.challenge_scalar("fixed base separation challenge");
   const HFr ch_var = tr.challenge_scalar("variable base separation challenge");
-  // public-input polynomial (prover.rs:519-521)
-  PB_CUDA(cudaMemsetAsync(pi_dense, 0, 2 * n * 32, st));
-  for (size_t i = 0; i < n_pi; i++)
-    PB_CUDA(cudaMemcpyAsync(pi_dense + 2 * pi_idx[i], PIV + i, 32, cudaMemcpyHostToDevice, st));
-  if (n_pi) PB_TRY(ntt_run((const uint64_t*)pi_dense, n, (uint64_t*)(pi_dense + 2 * n), log_n, 1, 0, 1, n, n, st, ar));
-  // coset evaluations: z, a, b, c, d, pi (quotient_poly.rs:50-59, 177)
-  PB_TRY(ntt_run((const uint64_t*)zp, n + 3, (uint64_t*)w8, log_n + 3, 0, 1, 5, stride, n8, st, ar));
-  if (n_pi)
-    PB_TRY(ntt_run((const uint64_t*)(pi_dense + 2 * n), n, (uint64_t*)(w8 + 2 * 5 * n8), log_n + 3, 0, 1, 1, n, n8, st, ar));
-  else
-    PB_CUDA(cudaMemsetAsync(w8 + 2 * 5 * n8, 0, n8 * 32, st));  // empty PI polynomial: 8n zeros
+  // coset evaluations of z, a, b, c, d and the public-input polynomial in one batch
+  // (quotient_poly.rs:50-59, 177)
+  PB_TRY(ntt_run((const uint64_t*)zp, n + 3, (uint64_t*)w8, log_n + 3, 0, 1, n_pi ? 6 : 5, stride, n8, st, ar));
+  if (!n_pi) PB_CUDA(cudaMemsetAsync(w8 + 2 * 5 * n8, 0, n8 * 32, st));  // empty PI polynomial: 8n zeros
   {
     QuotArgs q;
     q.w8 = w8; q.key8 = P->d_key8; q.linear8 = P->d_linear8; q.l1_8 = P->d_l1_8; q.out = quot; q.n8 = n8;
