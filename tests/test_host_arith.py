@@ -77,3 +77,45 @@ def test_g1_sum_and_mul(ht):
     for k in (0, 1, 2, 3, 0xDEADBEEFCAFEF00D):
         assert ht.ht_g1_mul_small(R.g1_to_raw_bytes(pts[2]), ctypes.c_uint64(k), out) == 0
         assert R.g1_from_raw_bytes(out.raw) == R.g1_mul(pts[2], k)
+
+
+@pytest.fixture(scope="module")
+def hp():
+    so = os.path.join(HERE, "hosttest", "libhostproduct.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, os.path.join(HERE, "hosttest", "hostproduct.cpp")])
+    return ctypes.CDLL(so)
+
+
+def test_product_transcript_matches_oracle(hp):
+    """plonk_b200/csrc/transcript.h (merlin/STROBE/Keccak + TranscriptProtocol) vs oracle/pyref.py."""
+    out = (ctypes.c_uint64 * 4)()
+    hp.hp_transcript_scalar(b"test protocol", b"some label", b"some data", ctypes.c_size_t(9), b"challenge", out)
+    t = R.Transcript(b"test protocol")
+    t.append_message(b"some label", b"some data")
+    assert R.fr_from_mont_bytes(bytes(out)) == t.challenge_scalar(b"challenge")
+    rng = random.Random(3)
+    for n in (5, 65530, 1 << 40):
+        s = rng.randrange(R.R_MOD)
+        hp.hp_transcript_mix(R.fr_to_mont_bytes(s), ctypes.c_uint64(n), out)
+        t = R.Transcript(b"mix")
+        t.circuit_domain_sep(n)
+        t.append_scalar(b"s", s)
+        t.append_commitment(b"c", None)
+        a = t.challenge_scalar(b"a")
+        t.append_scalar(b"a", a)
+        b = t.challenge_scalar(b"b")
+        assert R.fr_from_mont_bytes(bytes(out)) == (a * b + s) % R.R_MOD
+
+
+def test_product_host_field_and_compression(hp):
+    rng = random.Random(4)
+    Rm = 1 << 384
+    for _ in range(20):
+        x = rng.randrange(1, R.P_MOD)
+        out = (ctypes.c_uint64 * 6)()
+        hp.hp_fp_inv((x * Rm % R.P_MOD).to_bytes(48, "little"), out)
+        assert int.from_bytes(bytes(out), "little") == pow(x, -1, R.P_MOD) * Rm % R.P_MOD
+    for p in [None] + [R.g1_mul(R.G1_GEN, rng.randrange(1, R.R_MOD)) for _ in range(10)]:
+        out = ctypes.create_string_buffer(48)
+        hp.hp_g1_compress(R.g1_to_raw_bytes(p), out)
+        assert out.raw == R.g1_compress(p)
