@@ -37,8 +37,8 @@ struct pb200_srs {
 
 namespace pb {
 
-static constexpr int kGroup = 4;
-static constexpr unsigned kClassChunk = 256;  // members of a class summed by one warp
+static constexpr int kGroup = 8;
+static constexpr unsigned kClassChunk = 512;  // members of a class summed by one warp
 static constexpr unsigned kHeavy = 512;  // buckets longer than this many size units (~8x the average) get a whole CTA  // buckets per running-sum group in the reduction
 
 PB_D G1Affine ld_affine(const uint4* p, size_t i) {
