@@ -50,6 +50,38 @@ cudaStream_t thread_stream() {
   return st;
 }
 
+cudaError_t stream_wait(cudaStream_t st) {
+  static const bool spin = [] {
+    const char* e = getenv("PB200_SPIN");
+    return e && atoi(e) != 0;
+  }();
+  if (spin) return cudaStreamSynchronize(st);
+  static thread_local cudaEvent_t ev = nullptr;
+  if (!ev) {
+    cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+  }
+  cudaError_t e = cudaEventRecord(ev, st);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(ev);
+}
+
+void* pinned_scratch(size_t bytes, int slot) {
+  static thread_local void* bufs[2] = {nullptr, nullptr};
+  static thread_local size_t caps[2] = {0, 0};
+  void*& buf = bufs[slot & 1];
+  size_t& cap = caps[slot & 1];
+  if (bytes > cap) {
+    if (buf) cudaFreeHost(buf);
+    buf = nullptr;
+    cap = 0;
+    const size_t want = bytes < (64u << 10) ? (64u << 10) : bytes;
+    if (cudaHostAlloc(&buf, want, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    cap = want;
+  }
+  return buf;
+}
+
 int ntt_run(const uint64_t* d_in, size_t in_len, uint64_t* d_out, uint32_t log_n, int inverse, int coset,
             uint32_t batch, size_t in_stride, size_t out_stride, cudaStream_t st, Arena* ar);
 int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_t n, uint32_t batch,

@@ -46,6 +46,14 @@ inline int fail(int code, const char* what, const char* detail = "") {
 // The calling thread's pb200 stream (created on first use, never destroyed).
 cudaStream_t thread_stream();
 int ensure_init();
+// Host wait for everything enqueued on `st`.  Sleeps on a blocking-sync event instead of spinning in
+// cudaStreamSynchronize: a proving process keeps one host thread per proof in flight, and with 8 GPUs
+// x 8 proofs per box spinning threads would occupy every core of the host (PB200_SPIN=1 restores
+// the spinning wait).
+cudaError_t stream_wait(cudaStream_t st);
+// Per-thread pinned staging buffer for small device -> host results (an async copy into pageable
+// memory would make the driver wait inside the copy call).  Returns nullptr on failure.
+void* pinned_scratch(size_t bytes, int slot = 0);  // slot 0: MSM results, slot 1: prover scalars
 
 inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 

@@ -621,9 +621,11 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
             n_groups, plan, chunks, classes);
   PB_LAUNCH(k_msm_final, batch, 256, 0, st, (const uint4*)classes, plan, chunks, result);
   PB_CUDA(cudaGetLastError());
-  std::vector<uint32_t> host((size_t)batch * (plan.ndig + 1) * 48);
-  PB_CUDA(cudaMemcpyAsync(host.data(), result, host.size() * 4, cudaMemcpyDeviceToHost, st));
-  PB_CUDA(cudaStreamSynchronize(st));
+  const size_t host_words = (size_t)batch * (plan.ndig + 1) * 48;
+  uint32_t* host = (uint32_t*)pinned_scratch(host_words * 4);
+  if (!host) return fail(PB200_ERR_CUDA, "pinned staging buffer");
+  PB_CUDA(cudaMemcpyAsync(host, result, host_words * 4, cudaMemcpyDeviceToHost, st));
+  PB_CUDA(stream_wait(st));
   if (prof) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) {
@@ -650,7 +652,7 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
   // (Montgomery's trick over the ZZ*ZZZ of the batch's results).
   std::vector<pbh::HXyzz> res(batch);
   for (uint32_t b = 0; b < batch; b++) {
-    const uint32_t* hp = host.data() + (size_t)b * (plan.ndig + 1) * 48;
+    const uint32_t* hp = host + (size_t)b * (plan.ndig + 1) * 48;
     pbh::HXyzz h = pbh::HXyzz::identity(), t;
     for (int d = plan.ndig - 1; d >= 0; d--) {
       xyzz_dev_to_host(hp + (size_t)d * 48, &t);

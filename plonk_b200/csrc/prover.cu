@@ -690,7 +690,7 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
     Arena* a;
     cudaStream_t st;
     ~Release() {
-      cudaStreamSynchronize(st);  // error paths may leave work in flight
+      stream_wait(st);  // error paths may leave work in flight
       a->off = 0;
       std::lock_guard<std::mutex> lk(P->ws_mu);
       P->ws_free.push_back(*a);
@@ -789,8 +789,10 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
   PB_CUDA(cudaMemsetAsync(flag, 0, 4, st));
   PB_LAUNCH(k_any_nonzero, div_up(n8 - 7 * n, 256), 256, 0, st, (const uint4*)tcoef, 7 * n, n8, flag);
   PB_LAUNCH(k_split_quotient, dim3(div_up(stride, 256), 4), 256, 0, st, (const uint4*)tcoef, n, n8, stride, to_dev(BL[11]), to_dev(BL[12]), to_dev(BL[13]), tq);
-  unsigned h_flag = 0;
-  PB_CUDA(cudaMemcpyAsync(&h_flag, flag, 4, cudaMemcpyDeviceToHost, st));
+  unsigned char* stage = (unsigned char*)pinned_scratch(1024, 1);
+  if (!stage) return fail(PB200_ERR_CUDA, "pinned staging buffer");
+  volatile unsigned& h_flag = *(volatile unsigned*)(stage + 512);
+  PB_CUDA(cudaMemcpyAsync(stage + 512, flag, 4, cudaMemcpyDeviceToHost, st));
   const size_t key_len = srs_len(P->srs);
   const size_t tlen = std::min(stride, key_len);
   PB_TRY(msm_run(P->srs, 0, (const uint64_t*)tq, tlen, 4, stride, aff, st, ar));  // synchronises the stream
@@ -822,8 +824,9 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
     }
     PB_LAUNCH(k_poly_eval, dim3(eval_blocks, 15), 256, 0, st, jobs, partial, eval_blocks);
     PB_LAUNCH(k_sum_rows, 15, 32, 0, st, (const uint4*)partial, eval_blocks, evals_d);
-    PB_CUDA(cudaMemcpyAsync(ev, evals_d, 15 * 32, cudaMemcpyDeviceToHost, st));
-    PB_CUDA(cudaStreamSynchronize(st));
+    PB_CUDA(cudaMemcpyAsync(stage, evals_d, 15 * 32, cudaMemcpyDeviceToHost, st));
+    PB_CUDA(stream_wait(st));
+    memcpy(ev, stage, 15 * 32);
   }
   tr.append_scalar("a_eval", ev[E_A]); tr.append_scalar("b_eval", ev[E_B]); tr.append_scalar("c_eval", ev[E_C]); tr.append_scalar("d_eval", ev[E_D]);
   tr.append_scalar("s_sigma_1_eval", ev[E_S1]); tr.append_scalar("s_sigma_2_eval", ev[E_S2]); tr.append_scalar("s_sigma_3_eval", ev[E_S3]);
