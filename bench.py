@@ -90,10 +90,21 @@ def finish_dist(world):
         dist.destroy_process_group()
 
 
-def build_workload():
-    from plonk_b200.composer import synthetic_circuit
+def build_workload(circuit: str):
+    """Returns (arrays, description).  "bench" is the reference's own benchmark circuit
+    (benches/plonk.rs BenchCircuit<2^16>: 64129 gates of every gadget family), built by the native
+    composer of libplonk_b200; "synthetic" is a random arithmetic-gate circuit filling the domain."""
+    if circuit == "bench":
+        from plonk_b200.gadgets import bench_circuit
 
-    return synthetic_circuit(N_GATES, seed=16).arrays()
+        arrays = bench_circuit(1 << LOG_GATES).arrays()
+        what = f"reference BenchCircuit<2^16> (benches/plonk.rs: {arrays.constraints} gates of all gadget families"
+    else:
+        from plonk_b200.composer import synthetic_circuit
+
+        arrays = synthetic_circuit(N_GATES, seed=16).arrays()
+        what = f"2^16-gate synthetic arithmetic circuit ({arrays.constraints} constraints"
+    return arrays, what + ", domain 2^16, quotient domain 2^19)"
 
 
 def run_ours(args):
@@ -111,7 +122,7 @@ def run_ours(args):
 
     L = lib()
     check(L.pb200_init(local))
-    arrays = build_workload()
+    arrays, workload = build_workload(args.circuit)
     srs_raw = ctypes.create_string_buffer(SRS_POINTS * 96)
     check(L.pb200_srs_setup_from_secret(mont(SRS_X), mont(SRS_G), SRS_POINTS, srs_raw))
     prover = Prover(LABEL, arrays.constraints, arrays.selectors, arrays.wires, arrays.n_witnesses, srs_raw.raw)
@@ -225,8 +236,7 @@ def run_ours(args):
         "metric": "proofs/sec @ 2^16 gates", "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32 limbs (Fr 256-bit / Fp 384-bit Montgomery)", "data": "synthetic",
-        "config": {"workload": "2^16-gate arithmetic circuit (65530 constraints, domain 2^16, quotient domain 2^19), "
-                               "Proof bytes == CPU restatement of the reference (tests/test_gpu_prover.py)",
+        "config": {"workload": workload + "; Proof bytes == CPU restatement of the reference (tests/test_gpu_prover.py)",
                    "proofs_per_step_per_gpu": inflight, "parallelism": f"replicas x{world}, no collective",
                    "l2": "per-proof working set ~0.7 GB (prover key 240 MB + MSM tables 100 MB + scratch) > 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": inflight * (n_wit * 32 + n_pi * 32 + 14 * 32),
@@ -295,8 +305,20 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    arrays = build_workload()
     from oracle import cref
+
+    if args.circuit == "bench":
+        # the reference arm runs none of the product's code: the circuit comes from the oracle's own composer
+        # (byte-identical to the native one, tests/test_gadgets.py)
+        from oracle import gadgets as oracle_gadgets
+
+        comp = oracle_gadgets.GadgetComposer.initialized()
+        oracle_gadgets.bench_circuit(comp, 1 << LOG_GATES)
+        arrays = cref.CircuitArrays(comp)
+        workload = (f"reference BenchCircuit<2^16> (benches/plonk.rs: {arrays.constraints} gates of all gadget families, "
+                    "domain 2^16, quotient domain 2^19)")
+    else:
+        arrays, workload = build_workload(args.circuit)
 
     threads = cref.threads()
     srs = cref.srs_from_secret(SRS_POINTS, SRS_X, SRS_G)
@@ -313,7 +335,7 @@ def run_reference(args):
         "impl": "reference", "metric": "proofs/sec @ 2^16 gates", "value": value, "unit": "proofs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (CPU)", "data": "synthetic",
-        "config": {"workload": "2^16-gate arithmetic circuit (65530 constraints)", "proofs_per_step": 1},
+        "config": {"workload": workload, "proofs_per_step": 1},
         "cpu_baseline": {"value": value, "unit": "proofs/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -327,6 +349,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--inflight", type=int, default=int(os.environ.get("PB200_INFLIGHT", "8")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--circuit", default="bench", choices=["bench", "synthetic"],
+                    help="bench = the reference's BenchCircuit<2^16> (default); synthetic = random arithmetic gates")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 3

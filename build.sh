@@ -13,6 +13,7 @@ for f in capi ntt msm prover; do
   pids+=($!)
 done
 g++ -std=c++17 -O2 -fPIC -c -o $OBJ/host_field.o $SRC/host_field.cpp
+g++ -std=c++17 -O2 -fPIC -c -o $OBJ/composer.o $SRC/composer.cpp
 for p in "${pids[@]}"; do wait $p; done
-nvcc -shared -o "$OUT" $OBJ/capi.o $OBJ/ntt.o $OBJ/msm.o $OBJ/prover.o $OBJ/host_field.o
+nvcc -shared -o "$OUT" $OBJ/capi.o $OBJ/ntt.o $OBJ/msm.o $OBJ/prover.o $OBJ/host_field.o $OBJ/composer.o
 echo "built $OUT"

