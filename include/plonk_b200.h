@@ -45,7 +45,10 @@ typedef enum {
   PB200_ERR_DEGREE_TOO_LARGE = -3,/* Error::PolynomialDegreeTooLarge (key.rs:362-370) */
   PB200_ERR_INVALID_ARG = -4,
   PB200_ERR_UNSATISFIED = -5,     /* Error::CircuitUnsatisfied (quotient_poly.rs:132-134) */
-  PB200_ERR_NOT_READY = -6
+  PB200_ERR_NOT_READY = -6,
+  /* -7 .. -9: circuit front end, plonk_b200_composer.h */
+  PB200_ERR_POINT_MALFORMED = -10 /* dusk_bytes::Error::InvalidData / Error::PointMalformed: a G1 encoding that is
+                                     not canonical, not on the curve or not in the prime-order subgroup */
 } pb200_status;
 
 typedef struct pb200_srs pb200_srs_t;
@@ -93,6 +96,12 @@ int pb200_msm_g1_range(const pb200_srs_t* srs, size_t first, const uint64_t* sca
 int pb200_srs_setup_from_secret(const uint64_t* x, const uint64_t* g_scalar, size_t n_points,
                                 uint8_t* out_raw);
 
+/* CommitKey::from_slice / PublicParameters::from_slice (key.rs:319-326, srs.rs:163-178): decodes
+ * n_points 48-byte compressed points (G1Affine::from_bytes: zcash encoding, with the on-curve and -
+ * when check_subgroup != 0, as the reference always does - prime-order subgroup checks) into the
+ * 96-byte raw layout pb200_srs_upload / pb200_prover_new take.  The square roots and the subgroup
+ * checks run on the GPU, one thread per point.  PB200_ERR_POINT_MALFORMED names the first bad point. */
+int pb200_g1_decompress(const uint8_t* compressed, size_t n_points, int check_subgroup, uint8_t* out_raw);
 /* 48-byte compressed encoding of one affine point given in the 96-byte raw layout. */
 int pb200_g1_compress(const uint64_t* affine_raw, uint8_t out48[48]);
 /* out = a + b for two points in the 96-byte raw layout (host-side helper for multi-GPU reduction). */

@@ -15,6 +15,7 @@ PB200_ERR_INVALID_DOMAIN = -2
 PB200_ERR_DEGREE_TOO_LARGE = -3
 PB200_ERR_INVALID_ARG = -4
 PB200_ERR_UNSATISFIED = -5
+PB200_ERR_POINT_MALFORMED = -10
 
 _lib = None
 
@@ -24,7 +25,7 @@ EXPORTS = [
     "pb200_ntt", "pb200_ntt_dev",
     "pb200_srs_upload", "pb200_srs_free", "pb200_srs_len",
     "pb200_msm_g1", "pb200_msm_g1_dev", "pb200_msm_g1_range",
-    "pb200_g1_compress", "pb200_g1_add_affine", "pb200_srs_setup_from_secret",
+    "pb200_g1_compress", "pb200_g1_decompress", "pb200_g1_add_affine", "pb200_srs_setup_from_secret",
     "pb200_profile_enable", "pb200_profile_read",
     "pb200_prover_new", "pb200_prover_free", "pb200_prover_commitments", "pb200_prove", "pb200_prove_dev",
     "pb200_imad_peak", "pb200_selftest_fr_mul", "pb200_selftest_fp_mul",
@@ -78,6 +79,7 @@ def lib() -> ctypes.CDLL:
         L.pb200_msm_g1_dev.argtypes = L.pb200_msm_g1.argtypes + [c.c_void_p]
         L.pb200_msm_g1_range.argtypes = [c.c_void_p, c.c_size_t, c.c_void_p, c.c_size_t, c.c_void_p]
         L.pb200_g1_compress.argtypes = [c.c_void_p, c.c_void_p]
+        L.pb200_g1_decompress.argtypes = [c.c_void_p, c.c_size_t, c.c_int, c.c_void_p]
         L.pb200_g1_add_affine.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p]
         L.pb200_prover_new.argtypes = [c.c_void_p, c.c_size_t, c.c_size_t, c.c_void_p, c.c_void_p, c.c_size_t, c.c_void_p, c.c_size_t, c.POINTER(c.c_void_p)]
         L.pb200_prover_free.argtypes = [c.c_void_p]

@@ -91,6 +91,7 @@ int selftest_mul(int which, const uint64_t* a, const uint64_t* b, uint64_t* o, s
 int imad_peak(double* out);
 size_t srs_len(const pb200_srs* s);
 int srs_setup(const uint64_t* x_mont, const uint64_t* g_scalar_mont, size_t n, uint8_t* out_raw);
+int g1_decompress(const uint8_t* in, size_t n, int check_subgroup, uint8_t* out_raw);
 extern std::atomic<int> g_prof_on;
 extern std::atomic<uint64_t> g_prof_acc_ns, g_prof_acc_adds, g_prof_acc_launches, g_prof_acc_points;
 void srs_free(pb200_srs* s);
@@ -223,6 +224,13 @@ int pb200_g1_add_affine(const uint64_t* a_raw, const uint64_t* b_raw, uint64_t* 
   memcpy(out_raw, x.v, 48);
   memcpy(out_raw + 6, y.v, 48);
   return 0;
+}
+
+int pb200_g1_decompress(const uint8_t* compressed, size_t n_points, int check_subgroup, uint8_t* out_raw) {
+  PB_TRY(ensure_init());
+  if (!compressed || !out_raw) return fail(PB200_ERR_INVALID_ARG, "null argument");
+  if (!n_points) return 0;
+  return g1_decompress(compressed, n_points, check_subgroup, out_raw);
 }
 
 int pb200_srs_setup_from_secret(const uint64_t* x, const uint64_t* g_scalar, size_t n_points, uint8_t* out_raw) {

@@ -128,6 +128,89 @@ __global__ void __launch_bounds__(64) k_srs_setup(uint4* out, size_t n, Fr x, Fr
   st_affine(out, i, xyzz_to_affine(acc));
 }
 
+// G1Affine::from_slice for a whole commit key (CommitKey::from_slice, reference
+// src/commitment_scheme/kzg10/key.rs:319-326; PublicParameters::from_slice srs.rs:163-178): the
+// 48-byte zcash encoding (big-endian x; bit 7 compressed, bit 6 infinity, bit 5 "y is the larger
+// root") is decoded to the 96-byte raw layout.  One thread per point: canonical-x check, y =
+// (x^3 + 4)^((p+1)/4) (p = 3 mod 4), root check, sign selection and - as G1Affine::from_bytes does -
+// the prime-order subgroup check [r]P = O.  `bad` receives the smallest index of a malformed point.
+__global__ void __launch_bounds__(64) k_g1_decompress(const uint8_t* in, size_t n, int check_subgroup, uint4* out, unsigned* bad) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* b = in + 48 * i;
+  const unsigned flags = b[0];
+  Fp x;
+#pragma unroll
+  for (int k = 0; k < 12; k++) {
+    const int o = 44 - 4 * k;
+    x.v[k] = ((uint32_t)b[o] << 24) | ((uint32_t)b[o + 1] << 16) | ((uint32_t)b[o + 2] << 8) | (uint32_t)b[o + 3];
+  }
+  x.v[11] &= 0x1fffffffu;
+  bool ok = (flags & 0x80u) != 0;
+  G1Affine pt;
+  pt.x = Fp::zero();
+  pt.y = Fp::zero();
+  if (flags & 0x40u) {
+    ok = ok && x.is_zero() && !(flags & 0x20u);
+  } else {
+    bool lt = false;  // x < p, compared from the top limb
+#pragma unroll
+    for (int k = 11; k >= 0; k--) {
+      const uint32_t m = FpParams::MOD(k);
+      if (x.v[k] != m) {
+        lt = x.v[k] < m;
+        break;
+      }
+    }
+    ok = ok && lt;
+    if (ok) {
+      const Fp xm = x.to_mont();
+      const Fp four = Fp::one().dbl().dbl();
+      const Fp y2 = xm.sqr() * xm + four;
+      uint32_t e[12];  // (p + 1) / 4
+#pragma unroll
+      for (int k = 0; k < 12; k++) e[k] = FpParams::MOD(k);
+      e[0] += 1u;  // no carry: the low limb of p is 0xffffaaab
+#pragma unroll
+      for (int k = 0; k < 12; k++) e[k] = (e[k] >> 2) | (k < 11 ? e[k + 1] << 30 : 0u);
+      Fp y = y2.pow(e, 12);
+      ok = y.sqr() == y2;
+      // y is "the larger root" iff y > p - y as integers
+      const Fp yc = y.from_mont(), nc = y.neg().from_mont();
+      bool larger = false;
+#pragma unroll
+      for (int k = 11; k >= 0; k--) {
+        if (yc.v[k] != nc.v[k]) {
+          larger = yc.v[k] > nc.v[k];
+          break;
+        }
+      }
+      if (larger != ((flags & 0x20u) != 0)) y = y.neg();
+      pt.x = xm;
+      pt.y = y;
+      if (ok && check_subgroup) {
+        G1Xyzz acc = G1Xyzz::identity();
+#pragma unroll 1
+        for (int w = 7; w >= 0; w--) {
+          const uint32_t word = FrParams::MOD(w);
+#pragma unroll 1
+          for (int bit = 31; bit >= 0; bit--) {
+            acc = xyzz_dbl(acc);
+            if ((word >> bit) & 1u) xyzz_madd(acc, pt.x, pt.y);
+          }
+        }
+        ok = acc.is_inf();
+      }
+    }
+  }
+  if (!ok) {
+    atomicMin(bad, (unsigned)i);
+    pt.x = Fp::zero();
+    pt.y = Fp::zero();
+  }
+  st_affine(out, i, pt);
+}
+
 // Signed-digit recoding + bucket histogram.  ebkt/epos are [batch][W][n].
 __global__ void k_msm_digits(const uint4* scalars, size_t n, size_t stride, int c, int W, unsigned nb,
                              unsigned* counts, unsigned* ebkt, unsigned* epos) {
@@ -741,6 +824,36 @@ int srs_setup(const uint64_t* x_mont, const uint64_t* g_scalar_mont, size_t n, u
   PB_CUDA(cudaMemcpyAsync(out_raw, d, n * 96, cudaMemcpyDeviceToHost, st));
   PB_CUDA(cudaStreamSynchronize(st));
   cudaFree(d);
+  return 0;
+}
+
+int g1_decompress(const uint8_t* in, size_t n, int check_subgroup, uint8_t* out_raw) {
+  cudaStream_t st = thread_stream();
+  uint8_t* d_in = nullptr;
+  uint4* d_out = nullptr;
+  unsigned* d_bad = nullptr;
+  PB_CUDA(cudaMalloc((void**)&d_in, n * 48));
+  PB_CUDA(cudaMalloc((void**)&d_out, n * 96));
+  PB_CUDA(cudaMalloc((void**)&d_bad, 4));
+  unsigned bad = 0xffffffffu;
+  cudaError_t e = cudaMemcpyAsync(d_in, in, n * 48, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0xff, 4, st);
+  if (e == cudaSuccess) {
+    PB_LAUNCH(k_g1_decompress, div_up(n, 64), 64, 0, st, d_in, n, check_subgroup, d_out, d_bad);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_raw, d_out, n * 96, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_in);
+  cudaFree(d_out);
+  cudaFree(d_bad);
+  PB_CUDA(e);
+  if (bad != 0xffffffffu) {
+    char msg[64];
+    snprintf(msg, sizeof msg, "point %u", bad);
+    return fail(PB200_ERR_POINT_MALFORMED, "malformed G1 encoding (not canonical, not on the curve or not in the subgroup)", msg);
+  }
   return 0;
 }
 

@@ -232,6 +232,10 @@ __global__ void k_scan_fixup(uint4* out, size_t n, const uint4* block_prefix) {
 // ---------------------------------------------------------------------------------------------
 // Quotient numerator on the 8n coset (quotient_poly.rs:160-310 + all widget compute_quotient_i)
 // ---------------------------------------------------------------------------------------------
+struct WidgetCh {
+  Fr ch, k, k2, k3, k4;
+};
+
 struct QuotArgs {
   const uint4* w8;      // [6][8n]: z, a, b, c, d, pi coset evaluations
   const uint4* key8;    // [15][8n] prover-key coset evaluations (enum order)
@@ -239,15 +243,19 @@ struct QuotArgs {
   const uint4* l1_8;    // [8n] L_1 on the coset (without alpha^2)
   uint4* out;           // [8n]
   size_t n8;
-  Fr alpha, beta, gamma, alpha_sq, ch_range, ch_logic, ch_fixed, ch_var;
+  Fr alpha, beta, gamma, alpha_sq;
+  // separation challenges with their powers (kappa = ch^2, kappa^2, ...), computed once on the host
+  // instead of once per coset point
+  WidgetCh ch_range, ch_logic, ch_fixed, ch_var;
+  Fr edwards_d;  // dusk_jubjub::EDWARDS_D, Montgomery form
   Fr vh_inv[8];
   int has_range, has_logic, has_fixed, has_var;
 };
 
-PB_D Fr delta4(const Fr& f) {
+PB_D Fr delta4(const Fr& f) {  // f (f - 1)(f - 2)(f - 3) = g (g + 2) with g = f (f - 3): two products
   const Fr one = Fr::one();
-  Fr f1 = f - one, f2 = f1 - one, f3 = f2 - one;
-  return f * f1 * f2 * f3;
+  const Fr g = f * (f - one - one - one);
+  return g * (g + one + one);
 }
 PB_D Fr mul_small(const Fr& x, int k) {  // k * x for small positive k by additions
   Fr acc = Fr::zero(), p = x;
@@ -258,24 +266,18 @@ PB_D Fr mul_small(const Fr& x, int k) {  // k * x for small positive k by additi
   }
   return acc;
 }
-PB_D Fr edwards_d() {  // dusk_jubjub::EDWARDS_D = -(10240/10241) mod r, canonical limbs
-  Fr d;
-  d.v[0] = 0xd6343eb1u; d.v[1] = 0x01065fd6u; d.v[2] = 0x37579d26u; d.v[3] = 0x292d7f6du;
-  d.v[4] = 0xe6bd7fd4u; d.v[5] = 0xf5fd9207u; d.v[6] = 0x4bfa2b48u; d.v[7] = 0x2a9318e7u;
-  return d.to_mont();
-}
 
 struct WireVals {
   Fr a, b, c, d, a_w, b_w, d_w;
 };
-PB_D Fr widget_range(const Fr& ch, const WireVals& v) {  // range/proverkey.rs:32-57 (without selector)
-  Fr k = ch.sqr(), k2 = k.sqr(), k3 = k2 * k;
+PB_D Fr widget_range(const WidgetCh& s, const WireVals& v) {  // range/proverkey.rs:32-57 (without selector)
+  const Fr &ch = s.ch, &k = s.k, &k2 = s.k2, &k3 = s.k3;
   Fr t = delta4(v.c - mul_small(v.d, 4)) + delta4(v.b - mul_small(v.c, 4)) * k + delta4(v.a - mul_small(v.b, 4)) * k2 +
          delta4(v.d_w - mul_small(v.a, 4)) * k3;
   return t * ch;
 }
-PB_D Fr widget_logic(const Fr& ch, const Fr& q_c, const WireVals& v) {  // logic/proverkey.rs:34-71, 120-144
-  Fr k = ch.sqr(), k2 = k.sqr(), k3 = k2 * k, k4 = k3 * k;
+PB_D Fr widget_logic(const WidgetCh& s, const Fr& q_c, const WireVals& v) {  // logic/proverkey.rs:34-71, 120-144
+  const Fr &ch = s.ch, &k = s.k, &k2 = s.k2, &k3 = s.k3, &k4 = s.k4;
   Fr A = v.a_w - mul_small(v.a, 4), B = v.b_w - mul_small(v.b, 4), D = v.d_w - mul_small(v.d, 4);
   const Fr& w = v.c;
   Fr ab = A + B;
@@ -285,25 +287,25 @@ PB_D Fr widget_logic(const Fr& ch, const Fr& q_c, const WireVals& v) {  // logic
   Fr t = delta4(A) + delta4(B) * k + delta4(D) * k2 + (w - A * B) * k3 + (Bq + E) * k4;
   return t * ch;
 }
-PB_D Fr widget_fixed(const Fr& ch, const Fr& q_l, const Fr& q_r, const Fr& q_c, const WireVals& v) {  // fixed_base/proverkey.rs:39-103
+PB_D Fr widget_fixed(const WidgetCh& s, const Fr& ed, const Fr& q_l, const Fr& q_r, const Fr& q_c, const WireVals& v) {  // fixed_base/proverkey.rs:39-103
   const Fr one = Fr::one();
-  Fr k = ch.sqr(), k2 = k.sqr(), k3 = k2 * k;
+  const Fr &ch = s.ch, &k = s.k, &k2 = s.k2, &k3 = s.k3;
   Fr bit = v.d_w - v.d - v.d;
   Fr bit_c = bit * (bit - one) * (bit + one);
   Fr y_alpha = bit.sqr() * (q_r - one) + one, x_alpha = bit * q_l;
   Fr xy = (bit * q_c - v.c) * k;
-  Fr t = v.c * v.a * v.b * edwards_d();
+  Fr t = v.c * v.a * v.b * ed;
   Fr xa = ((v.a_w + v.a_w * t) - (v.a * y_alpha + v.b * x_alpha)) * k2;
   Fr ya = ((v.b_w - v.b_w * t) - (v.b * y_alpha + v.a * x_alpha)) * k3;
   return (bit_c + xa + ya + xy) * ch;
 }
-PB_D Fr widget_var(const Fr& ch, const WireVals& v) {  // curve_addition/proverkey.rs:33-79
-  Fr k = ch.sqr();
+PB_D Fr widget_var(const WidgetCh& s, const Fr& ed, const WireVals& v) {  // curve_addition/proverkey.rs:33-79
+  const Fr &ch = s.ch, &k = s.k;
   const Fr &x1 = v.a, &x3 = v.a_w, &y1 = v.b, &y3 = v.b_w, &x2 = v.c, &y2 = v.d, &x1y2 = v.d_w;
   Fr xy = x1 * y2 - x1y2, y1x2 = y1 * x2, y1y2 = y1 * y2, x1x2 = x1 * x2;
-  Fr t = edwards_d() * x1y2 * y1x2;
+  Fr t = ed * x1y2 * y1x2;
   Fr x3c = ((x1y2 + y1x2) - (x3 + x3 * t)) * k;
-  Fr y3c = ((y1y2 + x1x2) - (y3 - y3 * t)) * k.sqr();
+  Fr y3c = ((y1y2 + x1x2) - (y3 - y3 * t)) * s.k2;
   return (xy + x3c + y3c) * ch;
 }
 
@@ -324,8 +326,8 @@ __global__ void __launch_bounds__(128) k_quotient(QuotArgs q) {
   Fr t = (v.a * v.b * KEY(Q_M) + v.a * q_l + v.b * q_r + v.c * KEY(Q_O) + v.d * KEY(Q_F) + q_c) * KEY(Q_ARITH);
   if (q.has_range) t = t + widget_range(q.ch_range, v) * KEY(Q_RANGE);
   if (q.has_logic) t = t + widget_logic(q.ch_logic, q_c, v) * KEY(Q_LOGIC);
-  if (q.has_fixed) t = t + widget_fixed(q.ch_fixed, q_l, q_r, q_c, v) * KEY(Q_FIXED);
-  if (q.has_var) t = t + widget_var(q.ch_var, v) * KEY(Q_VAR);
+  if (q.has_fixed) t = t + widget_fixed(q.ch_fixed, q.edwards_d, q_l, q_r, q_c, v) * KEY(Q_FIXED);
+  if (q.has_var) t = t + widget_var(q.ch_var, q.edwards_d, v) * KEY(Q_VAR);
   t = t + pi;
   // permutation/proverkey.rs:40-125
   const Fr x = ldg_fr(q.linear8, i);
@@ -778,7 +780,14 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
     QuotArgs q;
     q.w8 = w8; q.key8 = P->d_key8; q.linear8 = P->d_linear8; q.l1_8 = P->d_l1_8; q.out = quot; q.n8 = n8;
     q.alpha = to_dev(alpha); q.beta = to_dev(beta); q.gamma = to_dev(gamma); q.alpha_sq = to_dev(alpha.sqr());
-    q.ch_range = to_dev(ch_range); q.ch_logic = to_dev(ch_logic); q.ch_fixed = to_dev(ch_fixed); q.ch_var = to_dev(ch_var);
+    auto powers = [](const HFr& ch) {
+      const HFr k = ch.sqr(), k2 = k.sqr(), k3 = k2 * k;
+      WidgetCh w;
+      w.ch = to_dev(ch); w.k = to_dev(k); w.k2 = to_dev(k2); w.k3 = to_dev(k3); w.k4 = to_dev(k3 * k);
+      return w;
+    };
+    q.ch_range = powers(ch_range); q.ch_logic = powers(ch_logic); q.ch_fixed = powers(ch_fixed); q.ch_var = powers(ch_var);
+    q.edwards_d = to_dev((HFr::from_u64(10240) * HFr::from_u64(10241).inv()).neg());
     for (int i = 0; i < 8; i++) q.vh_inv[i] = to_dev(P->vh_inv[i]);
     q.has_range = P->has_widget[0]; q.has_logic = P->has_widget[1]; q.has_fixed = P->has_widget[2]; q.has_var = P->has_widget[3];
     PB_LAUNCH(k_quotient, div_up(n8, 128), 128, 0, st, q);

@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import ctypes
 
-from ._lib import PB200_ERR_DEGREE_TOO_LARGE, Pb200Error, check, lib
+from ._lib import PB200_ERR_DEGREE_TOO_LARGE, PB200_ERR_POINT_MALFORMED, Pb200Error, check, lib
 
 G1_RAW_BYTES = 96
 FR_BYTES = 32
@@ -12,6 +12,35 @@ FR_BYTES = 32
 
 class PolynomialDegreeTooLarge(ValueError):
     """Error::PolynomialDegreeTooLarge (reference key.rs:362-370)."""
+
+
+class PointMalformed(ValueError):
+    """dusk_bytes::Error::InvalidData / Error::PointMalformed: a G1 encoding that is not canonical, not on
+    the curve or not in the prime-order subgroup (G1Affine::from_bytes)."""
+
+
+def g1_decompress(compressed: bytes, check_subgroup: bool = True) -> bytes:
+    """N x 48-byte compressed points -> N x 96-byte raw points (square roots and subgroup checks on the GPU)."""
+    if len(compressed) % 48:
+        raise PointMalformed("length is not a multiple of 48")  # chunks(G1Affine::SIZE) then from_slice fails
+    n = len(compressed) // 48
+    out = ctypes.create_string_buffer(max(n, 1) * G1_RAW_BYTES)
+    try:
+        check(lib().pb200_g1_decompress(compressed, n, 1 if check_subgroup else 0, out))
+    except Pb200Error as e:
+        if e.code == PB200_ERR_POINT_MALFORMED:
+            raise PointMalformed(str(e)) from e
+        raise
+    return out.raw[: n * G1_RAW_BYTES]
+
+
+def g1_compress(raw_points: bytes) -> bytes:
+    out = ctypes.create_string_buffer(48)
+    res = bytearray()
+    for i in range(0, len(raw_points), G1_RAW_BYTES):
+        check(lib().pb200_g1_compress(raw_points[i : i + G1_RAW_BYTES], out))
+        res += out.raw
+    return bytes(res)
 
 
 class Commitment:
@@ -40,6 +69,11 @@ class CommitKey:
         h = ctypes.c_void_p()
         check(lib().pb200_srs_upload(raw_points, self.n_points, ctypes.byref(h)))
         self._h = h
+
+    @classmethod
+    def from_slice(cls, compressed: bytes) -> "CommitKey":
+        """CommitKey::from_slice (key.rs:319-326): 48-byte compressed powers, validated like the reference."""
+        return cls(g1_decompress(compressed))
 
     def max_degree(self) -> int:
         return self.n_points - 1

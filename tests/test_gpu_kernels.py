@@ -211,3 +211,51 @@ def test_msm_skewed_scalars_heavy_buckets(pb):
         k = sum(si * (p0 + i * step) for i, si in enumerate(s)) % R.R_MOD
         assert R.g1_from_raw_bytes(g.raw) == R.g1_mul(R.G1_GEN, k)
     assert dt < 5.0, f"skewed MSM took {dt:.2f}s"
+
+
+def test_g1_decompress_matches_oracle_and_rejects_malformed_points(pb):
+    """CommitKey::from_slice (key.rs:319-326): compressed commit key -> raw points on the GPU."""
+    from plonk_b200.kzg import CommitKey, PointMalformed, g1_compress, g1_decompress
+
+    rng = random.Random(21)
+    pts = progression_bases(300, rng.randrange(1, R.R_MOD), rng.randrange(1, R.R_MOD)) + [None, R.G1_GEN, R.g1_neg(R.G1_GEN)]
+    comp = b"".join(R.g1_compress(p) for p in pts)
+    raw = g1_decompress(comp)
+    assert raw == bases_to_abi(pts)
+    assert g1_compress(raw) == comp  # and back through the product's own encoder
+    assert g1_decompress(b"") == b""
+    key = CommitKey.from_slice(comp[: 48 * 64])
+    coeffs = rand_fr(rng, 64)
+    assert R.g1_to_raw_bytes(R.jac_to_affine(R.msm_naive(pts[:64], coeffs))) == key.commit(to_abi(coeffs)).raw
+
+    def bad(i, enc, **kw):
+        blob = comp[: 48 * i] + enc + comp[48 * (i + 1) :]
+        with pytest.raises(PointMalformed) as e:
+            g1_decompress(blob, **kw)
+        assert f"point {i}" in str(e.value)
+
+    good = bytearray(R.g1_compress(pts[5]))
+    bad(5, bytes([good[0] & 0x7F]) + bytes(good[1:]))                      # compression flag missing
+    bad(7, bytes([0xC0]) + bytes(46) + b"\x01")                            # infinity with a non-zero x
+    bad(7, bytes([0xE0]) + bytes(47))                                      # infinity with the sort flag
+    bad(9, bytes([0x80 | 0x1A]) + (R.P_MOD.to_bytes(48, "big"))[1:])       # x = p: not canonical
+    x = 1
+    while pow((x ** 3 + 4) % R.P_MOD, (R.P_MOD - 1) // 2, R.P_MOD) == 1:
+        x += 1
+    bad(11, bytes([0x80]) + x.to_bytes(48, "big")[1:])                     # x^3 + 4 is not a square
+    # on the curve but outside the prime-order subgroup (the curve's cofactor is ~2^126)
+    x = 2
+    while True:
+        y2 = (x ** 3 + 4) % R.P_MOD
+        y = pow(y2, (R.P_MOD + 1) // 4, R.P_MOD)
+        if y * y % R.P_MOD == y2 and R.jac_to_affine(R.jac_mul(R.jac_from_affine((x, y)), R.R_MOD)) is not None:
+            break
+        x += 1
+    enc = R.g1_compress((x, y))
+    bad(299, enc)
+    blob = comp[: 48 * 299] + enc + comp[48 * 300 :]
+    assert g1_decompress(blob, check_subgroup=False)[96 * 299 : 96 * 300] == R.g1_to_raw_bytes((x, y))
+    # the first malformed point is the one reported
+    with pytest.raises(PointMalformed) as e:
+        g1_decompress(enc + comp[48:96] + bytes([0x00]) * 48)
+    assert "point 0" in str(e.value)
