@@ -13,6 +13,7 @@ proof's witnesses and the device -> host read of the proof.  The roofline block 
 dominant kernel (MSM bucket accumulation), timed live with CUDA events on its launching stream.
 """
 import argparse
+import math
 import ctypes
 import json
 import os
@@ -295,9 +296,27 @@ def cpu_baseline(arrays, n_proofs):
     for i in range(n_proofs):
         prover.prove(blinders_for(i), ca)
     dt = time.time() - t0
+    # the two kernels on their own, same sizes as the GPU microbenchmarks
+    import random
+
+    rng = random.Random(19)
+    n19 = 1 << (LOG_GATES + 3)
+    vec = b"".join(mont(rng.randrange(R_MOD)) for _ in range(1 << 12)) * (n19 >> 12)
+    t0 = time.time()
+    for _ in range(2):
+        cref.ntt(vec, LOG_GATES + 3, 0, 1)
+    ntt_s = (time.time() - t0) / 2
+    scalars = vec[: SRS_POINTS * 32]
+    t0 = time.time()
+    cref.msm(srs, scalars)
+    msm_s = time.time() - t0
+    window = int(math.log(SRS_POINTS)) + 2  # msm_variable_base's window rule
     return {"value": n_proofs / dt, "unit": "proofs/s", "cores": threads, "kind": "port",
             "sample": f"{n_proofs} proof(s) of the same 2^16-gate circuit, C++/OpenMP restatement of the reference prover "
-                      f"(the Rust crate cannot be built here: no cargo/rustc)"}
+                      f"(the Rust crate cannot be built here: no cargo/rustc)",
+            "coset_ntt_2^19": {"ms": ntt_s * 1e3, "butterflies_per_s": (n19 // 2) * (LOG_GATES + 3) / ntt_s},
+            "msm_2^16": {"ms": msm_s * 1e3, "points_per_s": SRS_POINTS / msm_s,
+                         "bucket_adds_per_s": SRS_POINTS * math.ceil(255 / window) / msm_s, "window_bits": window}}
 
 
 def run_reference(args):

@@ -83,7 +83,7 @@ def test_gpu_prover_all_gate_families(pb, log_gates, widgets):
         gpu.prove(bytes(bad), arrays.pi_idx, arrays.pi_vals, blinders)
 
 
-@pytest.mark.parametrize("degree", [1 << 5, 1 << 13, 1 << 16])
+@pytest.mark.parametrize("degree", [1 << 12, 1 << 13, 1 << 16])  # 2^12: BASELINE.json configs[0]
 def test_gpu_prover_reference_bench_circuit(pb, degree):
     """benches/plonk.rs BenchCircuit<DEGREE> (the circuit BASELINE.json's metric is quoted on): built
     by the product's native composer and proved on the GPU vs built by the oracle's composer and
