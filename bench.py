@@ -288,10 +288,10 @@ def cpu_baseline(arrays, n_proofs):
     """Restated reference (oracle/cref.cpp, all host threads) on a bounded sample of the same workload."""
     from oracle import cref
 
-    threads = cref.threads()
-    srs = cref.srs_from_secret(SRS_POINTS, SRS_X, SRS_G)
+    threads = cref.best_threads()
+    srs = cref.srs_from_secret(SRS_POINTS, SRS_X, SRS_G, threads)
     ca = arrays
-    prover = cref.CrefProver(LABEL, ca, srs)
+    prover = cref.CrefProver(LABEL, ca, srs, threads)
     t0 = time.time()
     for i in range(n_proofs):
         prover.prove(blinders_for(i), ca)
@@ -304,16 +304,17 @@ def cpu_baseline(arrays, n_proofs):
     vec = b"".join(mont(rng.randrange(R_MOD)) for _ in range(1 << 12)) * (n19 >> 12)
     t0 = time.time()
     for _ in range(2):
-        cref.ntt(vec, LOG_GATES + 3, 0, 1)
+        cref.ntt(vec, LOG_GATES + 3, 0, 1, threads)
     ntt_s = (time.time() - t0) / 2
     scalars = vec[: SRS_POINTS * 32]
     t0 = time.time()
-    cref.msm(srs, scalars)
+    cref.msm(srs, scalars, threads)
     msm_s = time.time() - t0
     window = int(math.log(SRS_POINTS)) + 2  # msm_variable_base's window rule
     return {"value": n_proofs / dt, "unit": "proofs/s", "cores": threads, "kind": "port",
             "sample": f"{n_proofs} proof(s) of the same 2^16-gate circuit, C++/OpenMP restatement of the reference prover "
-                      f"(the Rust crate cannot be built here: no cargo/rustc)",
+                      f"(the Rust crate cannot be built here: no cargo/rustc); "
+                      f"thread count = fastest of T, T/2, T/4 for the {cref.threads()} usable host threads",
             "coset_ntt_2^19": {"ms": ntt_s * 1e3, "butterflies_per_s": (n19 // 2) * (LOG_GATES + 3) / ntt_s},
             "msm_2^16": {"ms": msm_s * 1e3, "points_per_s": SRS_POINTS / msm_s,
                          "bucket_adds_per_s": SRS_POINTS * math.ceil(255 / window) / msm_s, "window_bits": window}}
@@ -339,9 +340,9 @@ def run_reference(args):
     else:
         arrays, workload = build_workload(args.circuit)
 
-    threads = cref.threads()
-    srs = cref.srs_from_secret(SRS_POINTS, SRS_X, SRS_G)
-    prover = cref.CrefProver(LABEL, arrays, srs)
+    threads = cref.best_threads()
+    srs = cref.srs_from_secret(SRS_POINTS, SRS_X, SRS_G, threads)
+    prover = cref.CrefProver(LABEL, arrays, srs, threads)
     for i in range(args.warmup):
         prover.prove(blinders_for(i), arrays)
     t0 = time.time()
@@ -349,7 +350,8 @@ def run_reference(args):
         prover.prove(blinders_for(1000 + i), arrays)
     dt = time.time() - t0
     value = args.steps / dt
-    sample = "each step = 1 proof of the 2^16-gate workload on all host threads (C++/OpenMP restatement; the Rust reference cannot be built here)"
+    sample = (f"each step = 1 proof of the 2^16-gate workload on {threads} host threads (fastest of T, T/2, T/4 for the "
+              f"{cref.threads()} usable ones; C++/OpenMP restatement; the Rust reference cannot be built here)")
     print(json.dumps({
         "impl": "reference", "metric": "proofs/sec @ 2^16 gates", "value": value, "unit": "proofs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,

@@ -51,6 +51,64 @@ def threads() -> int:
         return os.cpu_count() or 1
 
 
+def _cgroup_cpu_limit() -> Optional[int]:
+    """CPU bandwidth quota of this container (cgroup v2 cpu.max or v1 cfs quota), in whole CPUs."""
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            return max(1, -(-int(quota) // int(period)))
+    except (OSError, ValueError):
+        pass
+    try:
+        quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if quota > 0 and period > 0:
+            return max(1, -(-quota // period))
+    except (OSError, ValueError):
+        pass
+    return None
+
+
+_best_threads: Optional[int] = None
+
+
+def best_threads() -> int:
+    """Thread count at which the restated prover is fastest on this host: every core this process
+    may run on, capped by the container's CPU quota, and - because SMT siblings or a shared host can
+    make "all of them" slower than half - checked against T/2 and T/4 on a short NTT + MSM sample.
+    The CPU baseline should be the reference at its best, not at its most oversubscribed."""
+    global _best_threads
+    if _best_threads is not None:
+        return _best_threads
+    if os.environ.get("PB200_CPU_THREADS"):
+        _best_threads = threads()
+        return _best_threads
+    import time
+
+    top = threads()
+    limit = _cgroup_cpu_limit()
+    if limit:
+        top = min(top, limit)
+    cands = sorted({max(1, top), max(1, top // 2), max(1, top // 4)}, reverse=True)
+    if len(cands) == 1:
+        _best_threads = cands[0]
+        return _best_threads
+    n = 1 << 14
+    srs = srs_from_secret(n, 0x1234567, 0x7654321, cands[-1])
+    vec = b"".join(R.fr_to_mont_bytes((i * 0x9E3779B97F4A7C15 + 12345) % R.R_MOD) for i in range(1 << 10)) * ((1 << 17) >> 10)
+    best, best_t = cands[0], None
+    for t in cands:
+        ntt(vec, 17, 0, 1, t)  # warm the thread pool at this width
+        t0 = time.time()
+        ntt(vec, 17, 0, 1, t)
+        msm(srs, vec[: n * 32], t)
+        dt = time.time() - t0
+        if best_t is None or dt < best_t * 0.95:  # prefer more threads unless fewer is clearly faster
+            best, best_t = t, dt if best_t is None else min(dt, best_t)
+    _best_threads = best
+    return best
+
+
 def ntt(data: bytes, log_n: int, inverse: int, coset: int, nthreads: Optional[int] = None) -> bytes:
     out = ctypes.create_string_buffer(32 << log_n)
     lib().cref_ntt(data, len(data) // 32, out, log_n, inverse, coset, nthreads or threads())
