@@ -91,6 +91,16 @@ int pb200_msm_g1_dev(const pb200_srs_t* srs, const uint64_t* d_scalars, size_t n
 int pb200_msm_g1_range(const pb200_srs_t* srs, size_t first, const uint64_t* scalars,
                        size_t n_scalars, uint64_t* out_affine);
 
+/* One MSM whose points are partitioned across the GPUs of a box (BASELINE.json configs[3], SURVEY.md
+ * section 8e-ii): every rank calls this with its slice of the commit key (uploaded with
+ * pb200_srs_upload) and the matching slice of each scalar vector (host memory, `batch` vectors of
+ * stride `stride`).  The per-rank partial results - one affine point per batch entry - are exchanged
+ * with a single ncclAllGather on `nccl_comm` (an ncclComm_t of `n_ranks` ranks created by the caller;
+ * NCCL is looked up in the process at run time) and added locally in rank order, so every rank
+ * receives the same batch x 96-byte result.  This is the only collective on the path. */
+int pb200_msm_g1_allgather(const pb200_srs_t* srs_slice, const uint64_t* scalars_slice, size_t n_scalars,
+                           uint32_t batch, size_t stride, void* nccl_comm, int n_ranks, uint64_t* out_affine);
+
 /* PublicParameters::setup with explicit secrets (srs.rs:61-100): out[i] = [g_scalar * x^i] G1, as
  * n_points x 96-byte raw points.  Test/bench helper - a real SRS comes from a ceremony. */
 int pb200_srs_setup_from_secret(const uint64_t* x, const uint64_t* g_scalar, size_t n_points,

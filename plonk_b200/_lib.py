@@ -24,7 +24,7 @@ EXPORTS = [
     "pb200_init", "pb200_last_error", "pb200_device_sync", "pb200_launch_count",
     "pb200_ntt", "pb200_ntt_dev",
     "pb200_srs_upload", "pb200_srs_free", "pb200_srs_len",
-    "pb200_msm_g1", "pb200_msm_g1_dev", "pb200_msm_g1_range",
+    "pb200_msm_g1", "pb200_msm_g1_dev", "pb200_msm_g1_range", "pb200_msm_g1_allgather",
     "pb200_g1_compress", "pb200_g1_decompress", "pb200_g1_add_affine", "pb200_srs_setup_from_secret",
     "pb200_profile_enable", "pb200_profile_read",
     "pb200_prover_new", "pb200_prover_free", "pb200_prover_commitments", "pb200_prove", "pb200_prove_dev",
@@ -78,6 +78,7 @@ def lib() -> ctypes.CDLL:
         L.pb200_msm_g1.argtypes = [c.c_void_p, c.c_void_p, c.c_size_t, c.c_uint32, c.c_size_t, c.c_void_p]
         L.pb200_msm_g1_dev.argtypes = L.pb200_msm_g1.argtypes + [c.c_void_p]
         L.pb200_msm_g1_range.argtypes = [c.c_void_p, c.c_size_t, c.c_void_p, c.c_size_t, c.c_void_p]
+        L.pb200_msm_g1_allgather.argtypes = [c.c_void_p, c.c_void_p, c.c_size_t, c.c_uint32, c.c_size_t, c.c_void_p, c.c_int, c.c_void_p]
         L.pb200_g1_compress.argtypes = [c.c_void_p, c.c_void_p]
         L.pb200_g1_decompress.argtypes = [c.c_void_p, c.c_size_t, c.c_int, c.c_void_p]
         L.pb200_g1_add_affine.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p]

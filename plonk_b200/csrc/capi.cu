@@ -4,6 +4,10 @@
 #include <mutex>
 #include <vector>
 
+#include <dlfcn.h>
+
+#include <vector>
+
 #include "common.cuh"
 #include "host_field.h"
 
@@ -198,6 +202,69 @@ int pb200_msm_g1(const pb200_srs_t* srs, const uint64_t* scalars, size_t n_scala
 int pb200_msm_g1_range(const pb200_srs_t* srs, size_t first, const uint64_t* scalars, size_t n_scalars,
                        uint64_t* out_affine) {
   return msm_host(srs, first, scalars, n_scalars, 1, n_scalars, out_affine);
+}
+
+// ---- point-sharded MSM with an NCCL all-gather (BASELINE configs[3]) ----
+// NCCL is resolved at run time from the process (dlopen of libnccl.so.2: the copy the caller's
+// communicator was created with when one is already loaded), so that the library itself carries no
+// NCCL dependency and loads on hosts without it.
+namespace {
+typedef int (*nccl_all_gather_t)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef const char* (*nccl_error_string_t)(int);
+struct NcclApi {
+  nccl_all_gather_t all_gather = nullptr;
+  nccl_error_string_t error_string = nullptr;
+};
+const NcclApi* nccl_api() {
+  static const NcclApi api = [] {
+    NcclApi a;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+      a.all_gather = (nccl_all_gather_t)dlsym(h, "ncclAllGather");
+      a.error_string = (nccl_error_string_t)dlsym(h, "ncclGetErrorString");
+    }
+    return a;
+  }();
+  return api.all_gather ? &api : nullptr;
+}
+}  // namespace
+
+int pb200_msm_g1_allgather(const pb200_srs_t* srs_slice, const uint64_t* scalars_slice, size_t n_scalars, uint32_t batch,
+                           size_t stride, void* nccl_comm, int n_ranks, uint64_t* out_affine) {
+  PB_TRY(ensure_init());
+  if (!srs_slice || !out_affine || !nccl_comm || n_ranks < 1 || !batch) return fail(PB200_ERR_INVALID_ARG, "null or empty argument");
+  const NcclApi* nccl = nccl_api();
+  if (!nccl) return fail(PB200_ERR_NOT_READY, "libnccl.so.2 (ncclAllGather) is not available in this process");
+  // 1. this rank's partial sums over its slice of the key
+  std::vector<uint64_t> mine((size_t)batch * 12);
+  PB_TRY(msm_host(srs_slice, 0, scalars_slice, n_scalars, batch, stride, mine.data()));
+  // 2. the one exchange step: 96 bytes per batch entry and rank (a G1 addition is not an NCCL reduction)
+  cudaStream_t st = thread_stream();
+  const size_t part = (size_t)batch * 96;
+  uint8_t *d_send = nullptr, *d_recv = nullptr;
+  PB_CUDA(cudaMallocAsync((void**)&d_send, part, st));
+  PB_CUDA(cudaMallocAsync((void**)&d_recv, part * n_ranks, st));
+  std::vector<uint64_t> all((size_t)n_ranks * batch * 12);
+  cudaError_t e = cudaMemcpyAsync(d_send, mine.data(), part, cudaMemcpyHostToDevice, st);
+  int nrc = 0;
+  if (e == cudaSuccess) nrc = nccl->all_gather(d_send, d_recv, part, /*ncclUint8*/ 1, nccl_comm, st);
+  if (e == cudaSuccess && nrc == 0) e = cudaMemcpyAsync(all.data(), d_recv, part * n_ranks, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && nrc == 0) e = stream_wait(st);
+  cudaFreeAsync(d_send, st);
+  cudaFreeAsync(d_recv, st);
+  if (nrc != 0) return fail(PB200_ERR_CUDA, "ncclAllGather", nccl->error_string ? nccl->error_string(nrc) : "");
+  PB_CUDA(e);
+  // 3. every rank adds the partials in rank order
+  for (uint32_t b = 0; b < batch; b++) {
+    uint64_t acc[12] = {0};
+    for (int r = 0; r < n_ranks; r++) {
+      uint64_t sum[12];
+      PB_TRY(pb200_g1_add_affine(acc, all.data() + ((size_t)r * batch + b) * 12, sum));
+      memcpy(acc, sum, sizeof acc);
+    }
+    memcpy(out_affine + (size_t)b * 12, acc, sizeof acc);
+  }
+  return 0;
 }
 
 int pb200_g1_compress(const uint64_t* affine_raw, uint8_t out48[48]) {

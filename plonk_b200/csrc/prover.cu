@@ -252,13 +252,35 @@ struct QuotArgs {
   int has_range, has_logic, has_fixed, has_var;
 };
 
-PB_D Fr delta4(const Fr& f) {  // f (f - 1)(f - 2)(f - 3) = g (g + 2) with g = f (f - 3): two products
-  const Fr one = Fr::one();
-  const Fr g = f * (f - one - one - one);
+// The quotient kernel evaluates ~90 Fr products per coset point.  Fully inlined that is ~23 k
+// instructions per thread (~360 KB of SASS), several times what the instruction cache holds: ncu
+// showed its warps waiting for instructions (stall no_instruction 2.0 per issue, multiply pipe 29 %
+// busy).  Inside this kernel every product therefore goes through one out-of-line routine; `Q` is
+// Fr with that product.
+__device__ __noinline__ Fr fr_mul_outlined(Fr a, Fr b) { return a * b; }
+
+struct Q {
+  Fr v;
+  PB_D Q() {}
+  PB_D Q(const Fr& f) : v(f) {}
+  static PB_D Q one() { return Q(Fr::one()); }
+  static PB_D Q zero() { return Q(Fr::zero()); }
+  friend PB_D Q operator+(const Q& x, const Q& y) { return Q(x.v + y.v); }
+  friend PB_D Q operator-(const Q& x, const Q& y) { return Q(x.v - y.v); }
+  friend PB_D Q operator*(const Q& x, const Q& y) { return Q(fr_mul_outlined(x.v, y.v)); }
+  PB_D Q sqr() const { return Q(fr_mul_outlined(v, v)); }
+  PB_D Q dbl() const { return Q(v.dbl()); }
+};
+
+template <class F>
+PB_D F delta4(const F& f) {  // f (f - 1)(f - 2)(f - 3) = g (g + 2) with g = f (f - 3): two products
+  const F one = F::one();
+  const F g = f * (f - one - one - one);
   return g * (g + one + one);
 }
-PB_D Fr mul_small(const Fr& x, int k) {  // k * x for small positive k by additions
-  Fr acc = Fr::zero(), p = x;
+template <class F>
+PB_D F mul_small(const F& x, int k) {  // k * x for small positive k by additions
+  F acc = F::zero(), p = x;
   while (k) {
     if (k & 1) acc = acc + p;
     p = p.dbl();
@@ -268,44 +290,44 @@ PB_D Fr mul_small(const Fr& x, int k) {  // k * x for small positive k by additi
 }
 
 struct WireVals {
-  Fr a, b, c, d, a_w, b_w, d_w;
+  Q a, b, c, d, a_w, b_w, d_w;
 };
-PB_D Fr widget_range(const WidgetCh& s, const WireVals& v) {  // range/proverkey.rs:32-57 (without selector)
-  const Fr &ch = s.ch, &k = s.k, &k2 = s.k2, &k3 = s.k3;
-  Fr t = delta4(v.c - mul_small(v.d, 4)) + delta4(v.b - mul_small(v.c, 4)) * k + delta4(v.a - mul_small(v.b, 4)) * k2 +
+PB_D Q widget_range(const WidgetCh& s, const WireVals& v) {  // range/proverkey.rs:32-57 (without selector)
+  const Q &ch = s.ch, &k = s.k, &k2 = s.k2, &k3 = s.k3;
+  Q t = delta4(v.c - mul_small(v.d, 4)) + delta4(v.b - mul_small(v.c, 4)) * k + delta4(v.a - mul_small(v.b, 4)) * k2 +
          delta4(v.d_w - mul_small(v.a, 4)) * k3;
   return t * ch;
 }
-PB_D Fr widget_logic(const WidgetCh& s, const Fr& q_c, const WireVals& v) {  // logic/proverkey.rs:34-71, 120-144
-  const Fr &ch = s.ch, &k = s.k, &k2 = s.k2, &k3 = s.k3, &k4 = s.k4;
-  Fr A = v.a_w - mul_small(v.a, 4), B = v.b_w - mul_small(v.b, 4), D = v.d_w - mul_small(v.d, 4);
-  const Fr& w = v.c;
-  Fr ab = A + B;
-  Fr F = w * (w * (mul_small(w, 4) - mul_small(ab, 18) + fr_small(81)) + mul_small(A.sqr() + B.sqr(), 18) - mul_small(ab, 81) + fr_small(83));
-  Fr E = mul_small(ab + D, 3) - F.dbl();
-  Fr Bq = q_c * (mul_small(D, 9) - mul_small(ab, 3));
-  Fr t = delta4(A) + delta4(B) * k + delta4(D) * k2 + (w - A * B) * k3 + (Bq + E) * k4;
+PB_D Q widget_logic(const WidgetCh& s, const Q& q_c, const WireVals& v) {  // logic/proverkey.rs:34-71, 120-144
+  const Q &ch = s.ch, &k = s.k, &k2 = s.k2, &k3 = s.k3, &k4 = s.k4;
+  Q A = v.a_w - mul_small(v.a, 4), B = v.b_w - mul_small(v.b, 4), D = v.d_w - mul_small(v.d, 4);
+  const Q& w = v.c;
+  Q ab = A + B;
+  Q F = w * (w * (mul_small(w, 4) - mul_small(ab, 18) + mul_small(Q::one(), 81)) + mul_small(A.sqr() + B.sqr(), 18) - mul_small(ab, 81) + mul_small(Q::one(), 83));
+  Q E = mul_small(ab + D, 3) - F.dbl();
+  Q Bq = q_c * (mul_small(D, 9) - mul_small(ab, 3));
+  Q t = delta4(A) + delta4(B) * k + delta4(D) * k2 + (w - A * B) * k3 + (Bq + E) * k4;
   return t * ch;
 }
-PB_D Fr widget_fixed(const WidgetCh& s, const Fr& ed, const Fr& q_l, const Fr& q_r, const Fr& q_c, const WireVals& v) {  // fixed_base/proverkey.rs:39-103
-  const Fr one = Fr::one();
-  const Fr &ch = s.ch, &k = s.k, &k2 = s.k2, &k3 = s.k3;
-  Fr bit = v.d_w - v.d - v.d;
-  Fr bit_c = bit * (bit - one) * (bit + one);
-  Fr y_alpha = bit.sqr() * (q_r - one) + one, x_alpha = bit * q_l;
-  Fr xy = (bit * q_c - v.c) * k;
-  Fr t = v.c * v.a * v.b * ed;
-  Fr xa = ((v.a_w + v.a_w * t) - (v.a * y_alpha + v.b * x_alpha)) * k2;
-  Fr ya = ((v.b_w - v.b_w * t) - (v.b * y_alpha + v.a * x_alpha)) * k3;
+PB_D Q widget_fixed(const WidgetCh& s, const Q& ed, const Q& q_l, const Q& q_r, const Q& q_c, const WireVals& v) {  // fixed_base/proverkey.rs:39-103
+  const Q one = Q::one();
+  const Q &ch = s.ch, &k = s.k, &k2 = s.k2, &k3 = s.k3;
+  Q bit = v.d_w - v.d - v.d;
+  Q bit_c = bit * (bit - one) * (bit + one);
+  Q y_alpha = bit.sqr() * (q_r - one) + one, x_alpha = bit * q_l;
+  Q xy = (bit * q_c - v.c) * k;
+  Q t = v.c * v.a * v.b * ed;
+  Q xa = ((v.a_w + v.a_w * t) - (v.a * y_alpha + v.b * x_alpha)) * k2;
+  Q ya = ((v.b_w - v.b_w * t) - (v.b * y_alpha + v.a * x_alpha)) * k3;
   return (bit_c + xa + ya + xy) * ch;
 }
-PB_D Fr widget_var(const WidgetCh& s, const Fr& ed, const WireVals& v) {  // curve_addition/proverkey.rs:33-79
-  const Fr &ch = s.ch, &k = s.k;
-  const Fr &x1 = v.a, &x3 = v.a_w, &y1 = v.b, &y3 = v.b_w, &x2 = v.c, &y2 = v.d, &x1y2 = v.d_w;
-  Fr xy = x1 * y2 - x1y2, y1x2 = y1 * x2, y1y2 = y1 * y2, x1x2 = x1 * x2;
-  Fr t = ed * x1y2 * y1x2;
-  Fr x3c = ((x1y2 + y1x2) - (x3 + x3 * t)) * k;
-  Fr y3c = ((y1y2 + x1x2) - (y3 - y3 * t)) * s.k2;
+PB_D Q widget_var(const WidgetCh& s, const Q& ed, const WireVals& v) {  // curve_addition/proverkey.rs:33-79
+  const Q &ch = s.ch, &k = s.k;
+  const Q &x1 = v.a, &x3 = v.a_w, &y1 = v.b, &y3 = v.b_w, &x2 = v.c, &y2 = v.d, &x1y2 = v.d_w;
+  Q xy = x1 * y2 - x1y2, y1x2 = y1 * x2, y1y2 = y1 * y2, x1x2 = x1 * x2;
+  Q t = ed * x1y2 * y1x2;
+  Q x3c = ((x1y2 + y1x2) - (x3 + x3 * t)) * k;
+  Q y3c = ((y1y2 + x1x2) - (y3 - y3 * t)) * s.k2;
   return (xy + x3c + y3c) * ch;
 }
 
@@ -314,32 +336,33 @@ __global__ void __launch_bounds__(128) k_quotient(QuotArgs q) {
   if (i >= q.n8) return;
   const size_t n8 = q.n8, iw = (i + 8) & (n8 - 1);
   WireVals v;
-  const Fr z = ldg_fr(q.w8, i), z_w = ldg_fr(q.w8, iw);
+  const Q z = ldg_fr(q.w8, i), z_w = ldg_fr(q.w8, iw);
   v.a = ldg_fr(q.w8, n8 + i); v.a_w = ldg_fr(q.w8, n8 + iw);
   v.b = ldg_fr(q.w8, 2 * n8 + i); v.b_w = ldg_fr(q.w8, 2 * n8 + iw);
   v.c = ldg_fr(q.w8, 3 * n8 + i);
   v.d = ldg_fr(q.w8, 4 * n8 + i); v.d_w = ldg_fr(q.w8, 4 * n8 + iw);
-  const Fr pi = ldg_fr(q.w8, 5 * n8 + i);
+  const Q pi = ldg_fr(q.w8, 5 * n8 + i);
 #define KEY(k) ldg_fr(q.key8, (size_t)(k) * n8 + i)
-  const Fr q_l = KEY(Q_L), q_r = KEY(Q_R), q_c = KEY(Q_C);
+  const Q q_l = KEY(Q_L), q_r = KEY(Q_R), q_c = KEY(Q_C);
   // arithmetic/proverkey.rs:44-69
-  Fr t = (v.a * v.b * KEY(Q_M) + v.a * q_l + v.b * q_r + v.c * KEY(Q_O) + v.d * KEY(Q_F) + q_c) * KEY(Q_ARITH);
+  Q t = (v.a * v.b * KEY(Q_M) + v.a * q_l + v.b * q_r + v.c * KEY(Q_O) + v.d * KEY(Q_F) + q_c) * KEY(Q_ARITH);
   if (q.has_range) t = t + widget_range(q.ch_range, v) * KEY(Q_RANGE);
   if (q.has_logic) t = t + widget_logic(q.ch_logic, q_c, v) * KEY(Q_LOGIC);
   if (q.has_fixed) t = t + widget_fixed(q.ch_fixed, q.edwards_d, q_l, q_r, q_c, v) * KEY(Q_FIXED);
   if (q.has_var) t = t + widget_var(q.ch_var, q.edwards_d, v) * KEY(Q_VAR);
   t = t + pi;
   // permutation/proverkey.rs:40-125
-  const Fr x = ldg_fr(q.linear8, i);
-  const Fr bx = q.beta * x;
-  Fr ident = (v.a + bx + q.gamma) * (v.b + mul_small(bx, 7) + q.gamma) * (v.c + mul_small(bx, 13) + q.gamma) *
-             (v.d + mul_small(bx, 17) + q.gamma) * z * q.alpha;
-  Fr copy = (v.a + q.beta * KEY(S1) + q.gamma) * (v.b + q.beta * KEY(S2) + q.gamma) * (v.c + q.beta * KEY(S3) + q.gamma) *
-            (v.d + q.beta * KEY(S4) + q.gamma) * z_w * q.alpha;
+  const Q x = ldg_fr(q.linear8, i);
+  const Q alpha = q.alpha, beta = q.beta, gamma = q.gamma;
+  const Q bx = beta * x;
+  Q ident = (v.a + bx + gamma) * (v.b + mul_small(bx, 7) + gamma) * (v.c + mul_small(bx, 13) + gamma) *
+            (v.d + mul_small(bx, 17) + gamma) * z * alpha;
+  Q copy = (v.a + beta * KEY(S1) + gamma) * (v.b + beta * KEY(S2) + gamma) * (v.c + beta * KEY(S3) + gamma) *
+           (v.d + beta * KEY(S4) + gamma) * z_w * alpha;
 #undef KEY
-  Fr l1 = ldg_fr(q.l1_8, i) * q.alpha_sq;
-  t = t + ident - copy + (z - Fr::one()) * l1;
-  stg_fr(q.out, i, t * q.vh_inv[i & 7]);
+  Q l1 = Q(ldg_fr(q.l1_8, i)) * Q(q.alpha_sq);
+  t = t + ident - copy + (z - Q::one()) * l1;
+  stg_fr(q.out, i, (t * Q(q.vh_inv[i & 7])).v);
 }
 
 // flag |= any nonzero element in p[lo, hi)

@@ -77,3 +77,47 @@ def sharded_msm(key, scalars: bytes, device=None) -> bytes:
     sl = scalars[first * 32 : (first + count) * 32]
     check(lib().pb200_msm_g1_range(key._h, first, sl if count else None, count, out))
     return allgather_g1_sum(out.raw, device)
+
+
+class NcclComm:
+    """An ncclComm_t over the ranks of the default torch.distributed group, for the C ABI's
+    pb200_msm_g1_allgather (a host without torch creates one with ncclCommInitRank the same way).
+    The unique id travels through torch.distributed's own broadcast."""
+
+    class _UniqueId(ctypes.Structure):
+        _fields_ = [("internal", ctypes.c_char * 128)]
+
+    def __init__(self):
+        import torch.distributed as dist
+
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self._nccl = ctypes.CDLL("libnccl.so.2")  # the copy torch already loaded, if any
+        uid = self._UniqueId()
+        if self.rank == 0:
+            self._check(self._nccl.ncclGetUniqueId(ctypes.byref(uid)))
+        box = [bytes(uid.internal) if self.rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctypes.memmove(ctypes.byref(uid), box[0].ljust(128, b"\0"), 128)
+        self.handle = ctypes.c_void_p()
+        self._nccl.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, self._UniqueId, ctypes.c_int]
+        self._check(self._nccl.ncclCommInitRank(ctypes.byref(self.handle), self.world, uid, self.rank))
+
+    def _check(self, rc: int):
+        if rc != 0:
+            self._nccl.ncclGetErrorString.restype = ctypes.c_char_p
+            raise RuntimeError("NCCL: " + self._nccl.ncclGetErrorString(rc).decode())
+
+    def destroy(self):
+        if self.handle:
+            self._nccl.ncclCommDestroy.argtypes = [ctypes.c_void_p]
+            self._nccl.ncclCommDestroy(self.handle)
+            self.handle = None
+
+
+def sharded_msm_nccl(key_slice, scalars_slice: bytes, comm: NcclComm) -> bytes:
+    """pb200_msm_g1_allgather: `key_slice` is a CommitKey holding this rank's points only,
+    `scalars_slice` the matching coefficients.  Returns the 96-byte sum (same on every rank)."""
+    out = ctypes.create_string_buffer(G1_RAW_BYTES)
+    n = len(scalars_slice) // 32
+    check(lib().pb200_msm_g1_allgather(key_slice._h, scalars_slice if n else None, n, 1, max(n, 1), comm.handle, comm.world, out))
+    return out.raw

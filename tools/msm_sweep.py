@@ -30,6 +30,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sizes", default="16,18,20")
     ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--via", default="torch", choices=["torch", "capi"],
+                    help="torch: device-resident scalars + torch.distributed all_gather; capi: pb200_msm_g1_allgather "
+                         "(host scalars, ncclAllGather inside the C ABI on a communicator created here)")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
@@ -38,6 +41,9 @@ def main():
     L = lib()
     check(L.pb200_init(local))
     x, gs = 0x1234567, 0x7654321
+    comm = pd.NcclComm() if (args.via == "capi" and world > 1) else None
+    if args.via == "capi" and comm is None:
+        raise SystemExit("--via capi needs torchrun with at least 2 ranks")
     for log_n in (int(v) for v in args.sizes.split(",")):
         n = 1 << log_n
         first, count = pd.shard_range(n, rank, world)
@@ -57,8 +63,14 @@ def main():
             if world > 1:
                 dist.barrier()
             t0 = time.perf_counter()
-            check(L.pb200_msm_g1_dev(h, mine.data_ptr(), count, 1, count, out, None))
-            total = pd.allgather_g1_sum(out.raw, dev)
+            if comm is not None:
+                if it == 0:
+                    mine_host = mine.cpu().numpy().tobytes()
+                check(L.pb200_msm_g1_allgather(h, mine_host, count, 1, count, comm.handle, world, out))
+                total = out.raw
+            else:
+                check(L.pb200_msm_g1_dev(h, mine.data_ptr(), count, 1, count, out, None))
+                total = pd.allgather_g1_sum(out.raw, dev)
             torch.cuda.synchronize()
             ms = pd.max_over_ranks((time.perf_counter() - t0) * 1e3, dev)
             if it:
@@ -79,7 +91,9 @@ def main():
         if rank == 0:
             best = min(times)
             print(json.dumps({"log_n": log_n, "gpus": world, "ms": best, "points_per_s": n / best * 1e3,
-                              "checked": log_n <= 20}), flush=True)
+                              "checked": log_n <= 20, "via": args.via}), flush=True)
+    if comm is not None:
+        comm.destroy()
     if world > 1:
         dist.destroy_process_group()
 
