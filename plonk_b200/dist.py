@@ -95,9 +95,11 @@ class NcclComm:
         uid = self._UniqueId()
         if self.rank == 0:
             self._check(self._nccl.ncclGetUniqueId(ctypes.byref(uid)))
-        box = [bytes(uid.internal) if self.rank == 0 else None]
+        # string_at, not the field: ctypes hands a c_char array field back truncated at its first NUL
+        box = [ctypes.string_at(ctypes.addressof(uid), 128) if self.rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
-        ctypes.memmove(ctypes.byref(uid), box[0].ljust(128, b"\0"), 128)
+        assert len(box[0]) == 128
+        ctypes.memmove(ctypes.addressof(uid), box[0], 128)
         self.handle = ctypes.c_void_p()
         self._nccl.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, self._UniqueId, ctypes.c_int]
         self._check(self._nccl.ncclCommInitRank(ctypes.byref(self.handle), self.world, uid, self.rank))
