@@ -109,22 +109,29 @@ def best_threads() -> int:
     return best
 
 
+def _default_threads(work_items: int) -> int:
+    """Threads for a stand-alone call: small inputs stay narrow, large ones use the calibrated width."""
+    if work_items < (1 << 13):
+        return max(1, min(4, threads()))
+    return best_threads()
+
+
 def ntt(data: bytes, log_n: int, inverse: int, coset: int, nthreads: Optional[int] = None) -> bytes:
     out = ctypes.create_string_buffer(32 << log_n)
-    lib().cref_ntt(data, len(data) // 32, out, log_n, inverse, coset, nthreads or threads())
+    lib().cref_ntt(data, len(data) // 32, out, log_n, inverse, coset, nthreads or _default_threads(1 << log_n))
     return out.raw
 
 
 def msm(bases_raw: bytes, scalars: bytes, nthreads: Optional[int] = None) -> bytes:
     n = min(len(bases_raw) // 96, len(scalars) // 32)
     out = ctypes.create_string_buffer(96)
-    lib().cref_msm(bases_raw, scalars, n, out, nthreads or threads())
+    lib().cref_msm(bases_raw, scalars, n, out, nthreads or _default_threads(n))
     return out.raw
 
 
 def srs_from_secret(n: int, x: int, g_scalar: int, nthreads: Optional[int] = None) -> bytes:
     out = ctypes.create_string_buffer(96 * n)
-    lib().cref_srs_from_secret(n, R.fr_to_mont_bytes(x), R.fr_to_mont_bytes(g_scalar), out, nthreads or threads())
+    lib().cref_srs_from_secret(n, R.fr_to_mont_bytes(x), R.fr_to_mont_bytes(g_scalar), out, nthreads or _default_threads(n))
     return out.raw
 
 
@@ -156,8 +163,11 @@ def draw_blinders(rng: R.StdRng) -> bytes:
 class CrefProver:
     def __init__(self, label: bytes, arrays: CircuitArrays, srs_raw: bytes, nthreads: Optional[int] = None):
         self.arrays = arrays
+        if nthreads is None:
+            # small circuits gain nothing from a wide OpenMP team (and lose a lot on an oversubscribed host)
+            nthreads = max(1, min(best_threads(), arrays.constraints // 512))
         self._h = lib().cref_prover_new(label, len(label), arrays.constraints, arrays.selectors, arrays.wires,
-                                        arrays.n_witnesses, srs_raw, len(srs_raw) // 96, nthreads or threads())
+                                        arrays.n_witnesses, srs_raw, len(srs_raw) // 96, nthreads)
         if not self._h:
             raise ValueError("cref_prover_new failed (SRS too small?)")
 
