@@ -1,11 +1,9 @@
 // extern "C" surface of libplonk_b200 (see include/plonk_b200.h for the reference call sites each
 // entry point replaces).  Host-pointer variants stage through stream-ordered device allocations;
 // there is no CPU fallback anywhere: without a usable CUDA device every call returns PB200_ERR_CUDA.
-#include <mutex>
-#include <vector>
-
 #include <dlfcn.h>
 
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -146,11 +144,13 @@ int pb200_ntt(const uint64_t* in, size_t in_len, uint64_t* out, uint32_t log_n, 
   const size_t use = in_len < n ? in_len : n;
   uint64_t *d_in = nullptr, *d_out = nullptr;
   PB_CUDA(cudaMallocAsync((void**)&d_out, (size_t)batch * n * 32, st));
+  int rc = 0;
   if (use) {
-    PB_CUDA(cudaMallocAsync((void**)&d_in, (size_t)batch * use * 32, st));
-    PB_CUDA(cudaMemcpy2DAsync(d_in, use * 32, in, in_stride * 32, use * 32, batch, cudaMemcpyHostToDevice, st));
+    cudaError_t e = cudaMallocAsync((void**)&d_in, (size_t)batch * use * 32, st);
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(d_in, use * 32, in, in_stride * 32, use * 32, batch, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) rc = fail(PB200_ERR_CUDA, "ntt input upload", cudaGetErrorString(e));
   }
-  int rc = ntt_run(d_in, use, d_out, log_n, inverse, coset, batch, use, n, st, nullptr);
+  if (rc == 0) rc = ntt_run(d_in, use, d_out, log_n, inverse, coset, batch, use, n, st, nullptr);
   if (rc == 0) {
     cudaError_t e = cudaMemcpy2DAsync(out, out_stride * 32, d_out, n * 32, n * 32, batch, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -185,14 +185,13 @@ static int msm_host(const pb200_srs_t* srs, size_t first, const uint64_t* scalar
   if (!srs || !out || (!scalars && n)) return fail(PB200_ERR_INVALID_ARG, "null argument");
   if (first + n > srs_len(srs)) return fail(PB200_ERR_DEGREE_TOO_LARGE, "more scalars than commit-key points");
   cudaStream_t st = thread_stream();
+  ScratchScope scope(nullptr, st);
   uint64_t* d = nullptr;
   if (n && batch) {
-    PB_CUDA(cudaMallocAsync((void**)&d, (size_t)batch * n * 32, st));
+    PB_ALLOC(scope, d, (size_t)batch * n * 32);
     PB_CUDA(cudaMemcpy2DAsync(d, n * 32, scalars, stride * 32, n * 32, batch, cudaMemcpyHostToDevice, st));
   }
-  int rc = msm_run(srs, first, d, n, batch, n, out, st, nullptr);
-  if (d) cudaFreeAsync(d, st);
-  return rc;
+  return msm_run(srs, first, d, n, batch, n, out, st, nullptr);
 }
 
 int pb200_msm_g1(const pb200_srs_t* srs, const uint64_t* scalars, size_t n_scalars, uint32_t batch, size_t stride,
@@ -241,17 +240,16 @@ int pb200_msm_g1_allgather(const pb200_srs_t* srs_slice, const uint64_t* scalars
   // 2. the one exchange step: 96 bytes per batch entry and rank (a G1 addition is not an NCCL reduction)
   cudaStream_t st = thread_stream();
   const size_t part = (size_t)batch * 96;
+  ScratchScope scope(nullptr, st);
   uint8_t *d_send = nullptr, *d_recv = nullptr;
-  PB_CUDA(cudaMallocAsync((void**)&d_send, part, st));
-  PB_CUDA(cudaMallocAsync((void**)&d_recv, part * n_ranks, st));
+  PB_ALLOC(scope, d_send, part);
+  PB_ALLOC(scope, d_recv, part * n_ranks);
   std::vector<uint64_t> all((size_t)n_ranks * batch * 12);
   cudaError_t e = cudaMemcpyAsync(d_send, mine.data(), part, cudaMemcpyHostToDevice, st);
   int nrc = 0;
   if (e == cudaSuccess) nrc = nccl->all_gather(d_send, d_recv, part, /*ncclUint8*/ 1, nccl_comm, st);
   if (e == cudaSuccess && nrc == 0) e = cudaMemcpyAsync(all.data(), d_recv, part * n_ranks, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess && nrc == 0) e = stream_wait(st);
-  cudaFreeAsync(d_send, st);
-  cudaFreeAsync(d_recv, st);
   if (nrc != 0) return fail(PB200_ERR_CUDA, "ncclAllGather", nccl->error_string ? nccl->error_string(nrc) : "");
   PB_CUDA(e);
   // 3. every rank adds the partials in rank order

@@ -75,19 +75,37 @@ struct Arena {
   void reset(size_t m) { off = m; }
 };
 
-// ptr = arena block or stream-ordered allocation
-#define PB_ALLOC(ptr, bytes, st, ar)                                                        \
-  do {                                                                                      \
-    if (ar) {                                                                               \
-      *(void**)&(ptr) = (ar)->take(bytes);                                                  \
-      if (!(ptr)) return pb::fail(PB200_ERR_CUDA, "workspace arena exhausted", #ptr);       \
-    } else {                                                                                \
-      PB_CUDA(cudaMallocAsync((void**)&(ptr), (bytes), (st)));                              \
-    }                                                                                       \
-  } while (0)
-#define PB_FREE(ptr, st, ar)                 \
-  do {                                       \
-    if (!(ar) && (ptr)) cudaFreeAsync((ptr), (st)); \
+// Scratch of one call: blocks carved from the caller's arena, or stream-ordered pool allocations
+// when there is none.  Everything is released when the scope ends, on every exit path (arena: back
+// to the mark it started from; pool: cudaFreeAsync, which is ordered behind the work on `st`).
+struct ScratchScope {
+  Arena* ar;
+  cudaStream_t st;
+  size_t mark;
+  void* blocks[24];
+  int n_blocks = 0;
+  ScratchScope(Arena* a, cudaStream_t s) : ar(a), st(s), mark(a ? a->mark() : 0) {}
+  ~ScratchScope() { release(); }
+  ScratchScope(const ScratchScope&) = delete;
+  ScratchScope& operator=(const ScratchScope&) = delete;
+  void* take(size_t bytes) {
+    if (ar) return ar->take(bytes);
+    void* p = nullptr;
+    if (n_blocks == 24 || cudaMallocAsync(&p, bytes ? bytes : 1, st) != cudaSuccess) return nullptr;
+    blocks[n_blocks++] = p;
+    return p;
+  }
+  void release() {
+    if (ar) ar->reset(mark);
+    for (int i = 0; i < n_blocks; i++) cudaFreeAsync(blocks[i], st);
+    n_blocks = 0;
+  }
+};
+
+#define PB_ALLOC(scope, ptr, bytes)                                                                  \
+  do {                                                                                               \
+    *(void**)&(ptr) = (scope).take(bytes);                                                           \
+    if (!(ptr)) return pb::fail(PB200_ERR_CUDA, (scope).ar ? "workspace arena exhausted" : "device allocation failed", #ptr); \
   } while (0)
 
 }  // namespace pb

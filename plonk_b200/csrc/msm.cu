@@ -644,24 +644,24 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
     if (plan.ndig > 7) return fail(PB200_ERR_INVALID_ARG, "window too wide for the bucket reduction");
   }
 
-  const size_t ar_mark = ar ? ar->mark() : 0;
+  ScratchScope scope(ar, st);
   unsigned *counts = nullptr, *offsets = nullptr, *order = nullptr, *ebkt = nullptr, *epos = nullptr, *sorted = nullptr;
   uint4 *sums = nullptr, *classes = nullptr, *S = nullptr, *A = nullptr, *result = nullptr;
-  PB_ALLOC(counts, (size_t)batch * nb * 4, st, ar);
-  PB_ALLOC(offsets, (size_t)batch * (nb + 1) * 4, st, ar);
-  PB_ALLOC(order, (size_t)batch * nb * 4, st, ar);
+  PB_ALLOC(scope, counts, (size_t)batch * nb * 4);
+  PB_ALLOC(scope, offsets, (size_t)batch * (nb + 1) * 4);
+  PB_ALLOC(scope, order, (size_t)batch * nb * 4);
   unsigned* n_heavy = nullptr;
-  PB_ALLOC(n_heavy, (size_t)batch * 4, st, ar);
-  PB_ALLOC(ebkt, (size_t)batch * cap * 4, st, ar);
-  PB_ALLOC(epos, (size_t)batch * cap * 4, st, ar);
-  PB_ALLOC(sorted, (size_t)batch * cap * 4, st, ar);
-  PB_ALLOC(sums, (size_t)batch * nb * 192, st, ar);
+  PB_ALLOC(scope, n_heavy, (size_t)batch * 4);
+  PB_ALLOC(scope, ebkt, (size_t)batch * cap * 4);
+  PB_ALLOC(scope, epos, (size_t)batch * cap * 4);
+  PB_ALLOC(scope, sorted, (size_t)batch * cap * 4);
+  PB_ALLOC(scope, sums, (size_t)batch * nb * 192);
   unsigned chunks = 1;
   for (int j = 0; j < plan.ndig; j++) chunks = std::max<unsigned>(chunks, (unsigned)(((n_groups >> plan.bits[j]) + kClassChunk - 1) / kClassChunk));
-  PB_ALLOC(classes, (size_t)batch * plan.nclasses * chunks * 192, st, ar);
-  PB_ALLOC(S, (size_t)batch * n_groups * 192, st, ar);
-  PB_ALLOC(A, (size_t)batch * n_groups * 192, st, ar);
-  PB_ALLOC(result, (size_t)batch * (plan.ndig + 1) * 192, st, ar);
+  PB_ALLOC(scope, classes, (size_t)batch * plan.nclasses * chunks * 192);
+  PB_ALLOC(scope, S, (size_t)batch * n_groups * 192);
+  PB_ALLOC(scope, A, (size_t)batch * n_groups * 192);
+  PB_ALLOC(scope, result, (size_t)batch * (plan.ndig + 1) * 192);
   PB_CUDA(cudaMemsetAsync(counts, 0, (size_t)batch * nb * 4, st));
 
   PB_LAUNCH(k_msm_digits, dim3(div_up(n, 128), batch), 128, 0, st, (const uint4*)d_scalars, n, stride, c, W, nb,
@@ -722,13 +722,7 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
   }
-  if (ar) {
-    ar->reset(ar_mark);  // the stream was synchronised above: the scratch is dead
-  } else {
-    cudaFreeAsync(counts, st); cudaFreeAsync(offsets, st); cudaFreeAsync(order, st); cudaFreeAsync(n_heavy, st); cudaFreeAsync(ebkt, st);
-    cudaFreeAsync(epos, st); cudaFreeAsync(sorted, st); cudaFreeAsync(sums, st); cudaFreeAsync(classes, st);
-    cudaFreeAsync(S, st); cudaFreeAsync(A, st); cudaFreeAsync(result, st);
-  }
+  scope.release();  // the stream was synchronised above: the scratch is dead
 
   // Host tail: R = sum A_G + g * sum_j 2^shift_j D_j (Horner over the digits), then the affine
   // normalisation of Commitment::from (commitment.rs:89-93) with one shared inversion per batch

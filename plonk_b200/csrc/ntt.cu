@@ -382,8 +382,8 @@ int ntt_run(const uint64_t* d_in, size_t in_len, uint64_t* d_out, uint32_t log_n
   // pass writes the caller's buffer.  (A single pass is one CTA per vector: loads finish before
   // stores begin, so in == out is fine there.)
   uint64_t* d_tmp = nullptr;
-  const size_t ar_mark = ar ? ar->mark() : 0;
-  if (n_pass > 1) PB_ALLOC(d_tmp, (size_t)batch * n * 32, st, ar);
+  ScratchScope scope(ar, st);  // later users of this memory are ordered behind these kernels by the stream
+  if (n_pass > 1) PB_ALLOC(scope, d_tmp, (size_t)batch * n * 32);
 
   int log_h = 0;
   for (int q = 0; q < n_pass; q++) {
@@ -425,8 +425,6 @@ int ntt_run(const uint64_t* d_in, size_t in_len, uint64_t* d_out, uint32_t log_n
     PB_CUDA(cudaGetLastError());
     log_h += a.r;
   }
-  PB_FREE(d_tmp, st, ar);
-  if (ar) ar->reset(ar_mark);  // later users of this memory are ordered behind these kernels by the stream
   return 0;
 }
 

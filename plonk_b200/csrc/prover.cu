@@ -515,9 +515,9 @@ template <bool MUL, bool REV>
 static int fr_scan(const uint4* in, size_t n, uint4* out, cudaStream_t st, Arena* ar) {
   const unsigned nblk = div_up(n, 2048);
   uint4 *tot = nullptr, *tot_scan = nullptr;
-  const size_t ar_mark = ar ? ar->mark() : 0;
-  PB_ALLOC(tot, (size_t)nblk * 32, st, ar);
-  PB_ALLOC(tot_scan, (size_t)nblk * 32, st, ar);
+  ScratchScope scope(ar, st);
+  PB_ALLOC(scope, tot, (size_t)nblk * 32);
+  PB_ALLOC(scope, tot_scan, (size_t)nblk * 32);
   PB_LAUNCH((k_scan_local<MUL, REV>), nblk, 256, 0, st, in, n, out, tot);
   if (nblk > 1) {
     if (nblk > 2048) return fail(PB200_ERR_INVALID_ARG, "scan too large");
@@ -525,29 +525,35 @@ static int fr_scan(const uint4* in, size_t n, uint4* out, cudaStream_t st, Arena
     PB_LAUNCH((k_scan_fixup<MUL, REV>), div_up(n, 256), 256, 0, st, out, n, (const uint4*)tot_scan);
   }
   PB_CUDA(cudaGetLastError());
-  PB_FREE(tot, st, ar);
-  PB_FREE(tot_scan, st, ar);
-  if (ar) ar->reset(ar_mark);
   return 0;
 }
 
 static void compress_affine(const uint64_t* raw, uint8_t out[48]) { pbh::g1_compress_raw(raw, out); }
 
-int prover_new(const uint8_t* label, size_t label_len, size_t constraints, const uint64_t* selectors,
-               const uint32_t* wires, size_t n_witnesses, const uint8_t* srs_raw, size_t n_srs, pb200_prover** out) {
-  if (constraints == 0) return fail(PB200_ERR_INVALID_ARG, "empty circuit");
-  cudaStream_t st = thread_stream();
-  pb200_prover* P = new pb200_prover();
+void prover_free(pb200_prover* P);
+
+// Stream-ordered scratch that is returned to the pool on every exit path.
+struct PoolBlock {
+  void* p = nullptr;
+  cudaStream_t st;
+  explicit PoolBlock(cudaStream_t s) : st(s) {}
+  ~PoolBlock() {
+    if (p) cudaFreeAsync(p, st);
+  }
+  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes, st); }
+  PoolBlock(const PoolBlock&) = delete;
+  PoolBlock& operator=(const PoolBlock&) = delete;
+};
+
+static int prover_build(pb200_prover* P, const uint8_t* label, size_t label_len, size_t constraints, const uint64_t* selectors,
+                        const uint32_t* wires, size_t n_witnesses, const uint8_t* srs_raw, size_t n_srs, cudaStream_t st) {
   P->label.assign(label, label + label_len);
   P->constraints = constraints;
   P->n_witnesses = n_witnesses;
   size_t n_trim = 1;
   while (n_trim < constraints + 6) n_trim <<= 1;  // compiler.rs:121-124
   size_t keep = n_trim + 6;                       // srs.rs:188-196
-  if (keep + 1 > n_srs) {
-    delete P;
-    return fail(PB200_ERR_DEGREE_TOO_LARGE, "public parameters too small for this circuit (TruncatedDegreeTooLarge)");
-  }
+  if (keep + 1 > n_srs) return fail(PB200_ERR_DEGREE_TOO_LARGE, "public parameters too small for this circuit (TruncatedDegreeTooLarge)");
   size_t n = 1;
   int log_n = 0;
   while (n < constraints) {
@@ -557,10 +563,7 @@ int prover_new(const uint8_t* label, size_t label_len, size_t constraints, const
   P->n = n;
   P->n8 = 8 * n;
   P->log_n = log_n;
-  if (log_n + 3 >= 32) {
-    delete P;
-    return fail(PB200_ERR_INVALID_DOMAIN, "quotient domain too large");
-  }
+  if (log_n + 3 >= 32) return fail(PB200_ERR_INVALID_DOMAIN, "quotient domain too large");
   PB_TRY(srs_upload(srs_raw, keep + 1, &P->srs));
   const size_t n8 = P->n8;
   PB_CUDA(cudaMalloc((void**)&P->d_wires, 4 * constraints * 4));
@@ -572,8 +575,9 @@ int prover_new(const uint8_t* label, size_t label_len, size_t constraints, const
   PB_CUDA(cudaMemcpyAsync(P->d_wires, wires, 4 * constraints * 4, cudaMemcpyHostToDevice, st));
 
   // selector columns, zero padded to n, then iNTT -> coefficient form (compiler.rs:149-211)
-  uint4* cols = nullptr;
-  PB_CUDA(cudaMallocAsync((void**)&cols, (size_t)N_POLY * n * 32, st));
+  PoolBlock cols_block(st);
+  PB_CUDA(cols_block.alloc((size_t)N_POLY * n * 32));
+  uint4* cols = (uint4*)cols_block.p;
   PB_CUDA(cudaMemsetAsync(cols, 0, (size_t)N_POLY * n * 32, st));
   PB_CUDA(cudaMemcpy2DAsync(cols, n * 32, selectors, constraints * 32, constraints * 32, 11, cudaMemcpyHostToDevice, st));
   // sigma permutation on the host (composer/permutation.rs:106-141), Lagrange values on the device
@@ -595,14 +599,14 @@ int prover_new(const uint8_t* label, size_t label_len, size_t constraints, const
         const uint64_t cur = lst[i], nxt = lst[(i + 1) % lst.size()];
         sig[(size_t)(cur >> 40) * n + (cur & 0xffffffffffull)] = nxt;
       }
-    unsigned long long* d_sig = nullptr;
-    PB_CUDA(cudaMallocAsync((void**)&d_sig, 4 * n * 8, st));
+    PoolBlock sig_block(st);
+    PB_CUDA(sig_block.alloc(4 * n * 8));
+    unsigned long long* d_sig = (unsigned long long*)sig_block.p;
     PB_CUDA(cudaMemcpyAsync(d_sig, sig.data(), 4 * n * 8, cudaMemcpyHostToDevice, st));
     const uint4* w_half = nullptr;
     PB_TRY(get_twiddles(log_n, false, st, &w_half));
     PB_LAUNCH(k_sigma_lagrange, div_up(4 * n, 256), 256, 0, st, d_sig, n, w_half, cols + 2 * (size_t)S1 * n);
     PB_CUDA(cudaStreamSynchronize(st));  // sig (host vector) must outlive the copy
-    cudaFreeAsync(d_sig, st);
   }
   PB_TRY(ntt_run((const uint64_t*)cols, n, (uint64_t*)P->d_polys, log_n, 1, 0, N_POLY, n, n, st, nullptr));
   // commitments (compiler.rs:213-232): an all-zero selector commits to the identity
@@ -617,12 +621,12 @@ int prover_new(const uint8_t* label, size_t label_len, size_t constraints, const
   PB_TRY(ntt_run((const uint64_t*)P->d_polys, n, (uint64_t*)P->d_key8, log_n + 3, 0, 1, N_POLY, n, n8, st, nullptr));
   {
     HFr lin[2] = {HFr::zero(), HFr::one()};
-    uint4* d_lin = nullptr;
-    PB_CUDA(cudaMallocAsync((void**)&d_lin, 64, st));
+    PoolBlock lin_block(st);
+    PB_CUDA(lin_block.alloc(64));
+    uint4* d_lin = (uint4*)lin_block.p;
     PB_CUDA(cudaMemcpyAsync(d_lin, lin, 64, cudaMemcpyHostToDevice, st));
     PB_TRY(ntt_run((const uint64_t*)d_lin, 2, (uint64_t*)P->d_linear8, log_n + 3, 0, 1, 1, 2, n8, st, nullptr));
     PB_CUDA(cudaStreamSynchronize(st));
-    cudaFreeAsync(d_lin, st);
   }
   // vanishing polynomial on the coset has period 8 (domain.rs:340-351); its inverses are cached
   // (prover.rs:78-91).  L_1 on the coset: vh[i] * (8 / 8n) / (x_i - 1)  (quotient_poly.rs:265-284).
@@ -646,13 +650,24 @@ int prover_new(const uint8_t* label, size_t label_len, size_t constraints, const
   PB_TRY(ntt_run((const uint64_t*)(P->d_polys + 2 * (size_t)S1 * n), n, (uint64_t*)P->d_sigma, log_n, 0, 0, 4, n, n, st, nullptr));
   PB_CUDA(cudaGetLastError());
   PB_CUDA(cudaStreamSynchronize(st));
-  cudaFreeAsync(cols, st);
   {  // arena size for one proof: prover scratch + the larger of (NTT scratch, MSM scratch)
     const size_t stride = n + 8;
     const size_t elems = 8 * n + 16 * stride + 64 * n + 64 + 16 * (size_t)div_up(stride, 2048) + 4 * (size_t)div_up(stride, 2048);
     const size_t ntt_tmp = 6 * n8 * 32;
     const size_t msm_ws = msm_workspace_bytes(P->srs, std::min(stride, srs_len(P->srs)), 4);
     P->ws_bytes = elems * 32 + std::max(ntt_tmp, msm_ws) + (size_t)64 * 256 + (1 << 20);
+  }
+  return 0;
+}
+
+int prover_new(const uint8_t* label, size_t label_len, size_t constraints, const uint64_t* selectors,
+               const uint32_t* wires, size_t n_witnesses, const uint8_t* srs_raw, size_t n_srs, pb200_prover** out) {
+  if (constraints == 0) return fail(PB200_ERR_INVALID_ARG, "empty circuit");
+  pb200_prover* P = new pb200_prover();
+  const int rc = prover_build(P, label, label_len, constraints, selectors, wires, n_witnesses, srs_raw, n_srs, thread_stream());
+  if (rc != 0) {
+    prover_free(P);  // releases whatever had been allocated; the error message is already set
+    return rc;
   }
   *out = P;
   return 0;
@@ -722,25 +737,26 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
     }
   } release{P, &arena, st};
   Arena* ar = &arena;
+  ScratchScope scope(ar, st);
   uint4 *wv, *wp, *zp, *num, *den, *w8, *quot, *tcoef, *tq, *pi_dense, *agg, *pw, *scratch, *evals_d, *partial;
   unsigned* flag;
   const unsigned eval_blocks = div_up(stride, 2048);
-  PB_ALLOC(wv, 5 * n * 32, st, ar);       // wire values a, b, c, d and the dense public-input vector
-  PB_ALLOC(zp, 6 * stride * 32, st, ar);  // [z, a, b, c, d, pi] coefficient form: one coset-NTT batch in round 3
+  PB_ALLOC(scope, wv, 5 * n * 32);       // wire values a, b, c, d and the dense public-input vector
+  PB_ALLOC(scope, zp, 6 * stride * 32);  // [z, a, b, c, d, pi] coefficient form: one coset-NTT batch in round 3
   wp = zp + 2 * stride;
-  PB_ALLOC(num, n * 32, st, ar);
-  PB_ALLOC(den, n * 32, st, ar);
-  PB_ALLOC(w8, 6 * n8 * 32, st, ar);
-  PB_ALLOC(quot, n8 * 32, st, ar);
-  PB_ALLOC(tcoef, n8 * 32, st, ar);
-  PB_ALLOC(tq, 4 * stride * 32, st, ar);
+  PB_ALLOC(scope, num, n * 32);
+  PB_ALLOC(scope, den, n * 32);
+  PB_ALLOC(scope, w8, 6 * n8 * 32);
+  PB_ALLOC(scope, quot, n8 * 32);
+  PB_ALLOC(scope, tcoef, n8 * 32);
+  PB_ALLOC(scope, tq, 4 * stride * 32);
   pi_dense = wv + 2 * 4 * n;
-  PB_ALLOC(agg, 2 * stride * 32, st, ar);
-  PB_ALLOC(pw, 2 * stride * 32, st, ar);
-  PB_ALLOC(scratch, 2 * stride * 32, st, ar);
-  PB_ALLOC(evals_d, 16 * 32, st, ar);
-  PB_ALLOC(partial, (size_t)16 * eval_blocks * 32, st, ar);
-  PB_ALLOC(flag, 4, st, ar);
+  PB_ALLOC(scope, agg, 2 * stride * 32);
+  PB_ALLOC(scope, pw, 2 * stride * 32);
+  PB_ALLOC(scope, scratch, 2 * stride * 32);
+  PB_ALLOC(scope, evals_d, 16 * 32);
+  PB_ALLOC(scope, partial, (size_t)16 * eval_blocks * 32);
+  PB_ALLOC(scope, flag, 4);
 
   uint64_t aff[4 * 12];
   uint8_t c48[11][48];
@@ -1018,8 +1034,12 @@ int pb200_prove(const pb200_prover_t* p, const uint64_t* witnesses, size_t n_wit
   cudaStream_t st = thread_stream();
   uint64_t* d_wit = nullptr;
   PB_CUDA(cudaMallocAsync((void**)&d_wit, n_witnesses * 32, st));
-  PB_CUDA(cudaMemcpyAsync(d_wit, witnesses, n_witnesses * 32, cudaMemcpyHostToDevice, st));
-  int rc = prove_dev(p, d_wit, pi_idx, pi_vals, n_pi, blinders, out_proof, st);
+  int rc;
+  const cudaError_t e = cudaMemcpyAsync(d_wit, witnesses, n_witnesses * 32, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess)
+    rc = fail(PB200_ERR_CUDA, "witness upload", cudaGetErrorString(e));
+  else
+    rc = prove_dev(p, d_wit, pi_idx, pi_vals, n_pi, blinders, out_proof, st);
   cudaFreeAsync(d_wit, st);
   return rc;
 }
