@@ -75,7 +75,7 @@ def test_ntt_edge_vectors_and_closed_forms(pb):
     assert lin == [R.GENERATOR * pow(r8.group_gen, i, R.R_MOD) % R.R_MOD for i in range(1 << 8)]
 
 
-@pytest.mark.parametrize("log_n", [16, 19, 20])
+@pytest.mark.parametrize("log_n", [16, 19, 20, 23])  # 2^23: the quotient domain of a 2^20-gate circuit
 def test_ntt_large_properties(pb, log_n):
     """Sizes the Python oracle cannot reach in seconds: size-independent properties + spot checks
     of single outputs against the definition of the DFT (Horner evaluation at w^k)."""
@@ -189,6 +189,25 @@ def test_msm_2_20_points_against_known_secret(pb):
         check(lib().pb200_msm_g1_range(key._h, first, to_abi(poly[first : first + count]), count, out))
         parts.append(out.raw)
     assert pd.g1_sum(parts) == got.raw
+
+
+def test_msm_2_22_points_against_known_secret(pb):
+    """BASELINE.json configs[3] upper range on one GPU: 2^22 points, 20-bit windows.  The scalars are
+    64-bit-limb patterns cheap to build on the host; the result must equal [p(x)] g."""
+    from plonk_b200._lib import check, lib
+
+    rng = random.Random(22)
+    n = 1 << 22
+    x, gs = rng.randrange(1, R.R_MOD), rng.randrange(1, R.R_MOD)
+    raw = ctypes.create_string_buffer(96 * n)
+    check(lib().pb200_srs_setup_from_secret(R.fr_to_mont_bytes(x), R.fr_to_mont_bytes(gs), n, raw))
+    key = pb.CommitKey(raw.raw)
+    del raw
+    block = rand_fr(rng, 1 << 12)  # the coefficient vector repeats a 4096-element block: p(x) = B(x) * sum_j x^(4096 j)
+    scalars = to_abi(block) * (n >> 12)
+    got = key.commit(scalars)
+    geo = (pow(x, n, R.R_MOD) - 1) * pow(pow(x, 1 << 12, R.R_MOD) - 1, -1, R.R_MOD) % R.R_MOD
+    assert R.g1_from_raw_bytes(got.raw) == R.g1_mul(R.g1_mul(R.G1_GEN, gs), R.poly_eval(block, x) * geo % R.R_MOD)
 
 
 def test_msm_skewed_scalars_heavy_buckets(pb):
