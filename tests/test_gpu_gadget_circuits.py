@@ -15,6 +15,7 @@ import pytest
 from oracle import cref
 from oracle import gadgets as G
 from oracle import pyref as R
+from oracle import verify as V
 
 pytestmark = pytest.mark.gpu
 
@@ -175,17 +176,23 @@ def test_gadget_circuit(pb, name, build, default, satisfied, unsatisfied):
     assert G.unsatisfied_rows(o) == [], "the default circuit must be satisfied"
     assert (narr.selectors, narr.wires, narr.witnesses) == (oarr.selectors, oarr.wires, oarr.witnesses)
     n = 1 << (oarr.constraints + 6 - 1).bit_length()  # pp.trim(next_pow2(constraints + 6)), compiler.rs:121-124
-    srs_raw = cref.srs_from_secret(n + 7, 0x5EED + len(name), 0xACE)
+    secret = 0x5EED + len(name)
+    srs_raw = cref.srs_from_secret(n + 7, secret, 0xACE)
     label = name.encode()
     cpu = cref.CrefProver(label, oarr, srs_raw)
     gpu = pb.Prover(label, narr.constraints, narr.selectors, narr.wires, narr.n_witnesses, srs_raw)
     assert gpu.commitments() == cpu.commitments()
+    key_comms = {k: R.g1_decompress(c) for k, c in zip(R.POLY_NAMES, gpu.commitments())}
+    g = R.g1_from_raw_bytes(srs_raw[:96])
     for k, vals in enumerate([default] + satisfied):
         o, oa, na = both(vals)
         assert (na.selectors, na.wires) == (narr.selectors, narr.wires), "gate layout must not depend on the witness"
         assert G.unsatisfied_rows(o) == [], vals
         blinders = cref.draw_blinders(R.StdRng.seed_from_u64(100 + k))
-        assert gpu.prove(na.witnesses, na.pi_idx, na.pi_vals, blinders) == cpu.prove(blinders, oa), vals
+        proof = gpu.prove(na.witnesses, na.pi_idx, na.pi_vals, blinders)
+        assert proof == cpu.prove(blinders, oa), vals
+        # and the GPU-made proof satisfies the reference Verifier's equation (oracle/verify.py)
+        assert V.verify_with_secret(proof, label, oarr.constraints, key_comms, o.public_input_indexes(), o.public_inputs_vec(), g, secret), vals
     for k, vals in enumerate(unsatisfied):
         o, oa, na = both(vals)
         assert (na.selectors, na.wires) == (narr.selectors, narr.wires)
