@@ -278,3 +278,45 @@ def test_g1_decompress_matches_oracle_and_rejects_malformed_points(pb):
     with pytest.raises(PointMalformed) as e:
         g1_decompress(enc + comp[48:96] + bytes([0x00]) * 48)
     assert "point 0" in str(e.value)
+
+
+def test_kzg_open_and_check_with_gpu_commitments(pb):
+    """key.rs:826-1018 (test_basic_commit, test_aggregate_witness) on the GPU MSM: commitments and
+    opening witnesses are committed with CommitKey.commit; the reference's pairing check
+    e(C - [v]g, H) == e(W, [x - z]H) is the G1 identity C - [v]g == [x - z]W under the known secret."""
+    rng = random.Random(826)
+    x, gs = rng.randrange(1, R.R_MOD), rng.randrange(1, R.R_MOD)
+    pts = R.srs_from_secret(28 + 1, x, gs)
+    key = pb.CommitKey(bases_to_abi(pts))
+    g = pts[0]
+    z = 10
+
+    def commit(poly):
+        return R.g1_from_raw_bytes(key.commit(to_abi(poly)).raw)
+
+    def check(c, v, w):  # OpeningKey::check (key.rs:489-507)
+        lhs = R.g1_add(c, R.g1_neg(R.g1_mul(g, v))) if v else c
+        return lhs == R.g1_mul(w, (x - z) % R.R_MOD)
+
+    # open_single (key.rs:743-760): witness = (p - v) / (X - z)
+    poly = rand_fr(rng, 26)
+    v = R.poly_eval(poly, z)
+    w = commit(R.ruffini(poly, z))  # ruffini drops the remainder, which is p(z)
+    assert check(commit(poly), v, w)
+    assert not check(commit(poly), (v + 1) % R.R_MOD, w)
+    # open_multiple / compute_aggregate_witness (key.rs:394-417, 762-794): sum_k v^k p_k, one witness
+    polys = [rand_fr(rng, 26), rand_fr(rng, 28), rand_fr(rng, 28)]
+    vch = rng.randrange(R.R_MOD)
+    agg = [0] * 28
+    power = 1
+    for p in polys:
+        for i, c in enumerate(p):
+            agg[i] = (agg[i] + c * power) % R.R_MOD
+        power = power * vch % R.R_MOD
+    w = commit(R.ruffini(agg, z))
+    flat_c, flat_v, power = None, 0, 1
+    for p in polys:  # AggregateProof::flatten (commitment_scheme/kzg10/proof.rs)
+        flat_c = R.g1_mul(commit(p), power) if flat_c is None else R.g1_add(flat_c, R.g1_mul(commit(p), power))
+        flat_v = (flat_v + R.poly_eval(p, z) * power) % R.R_MOD
+        power = power * vch % R.R_MOD
+    assert check(flat_c, flat_v, w)
