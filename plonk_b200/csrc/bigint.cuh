@@ -217,24 +217,43 @@ struct Field {
     else
       mad_pair<CIN, COUT>(lo, hi, a, b, clo, chi);
   }
-  template <bool FIRST>
-  static PB_HD void mont_row(uint32_t* X /* old E -> new O */, uint32_t* Y /* old O -> new E */,
-                             const uint32_t* a, uint32_t bi) {
-    constexpr bool S0 = (PB_SPLIT & 1) != 0, S1 = (PB_SPLIT & 2) != 0, S2 = (PB_SPLIT & 4) != 0, S3 = (PB_SPLIT & 8) != 0;
-    if (!FIRST) {
-      Y[0] = add_cc(Y[0], X[1]);
+  // One row of the product: T += a * bi.  On entry X is the old E (its low limb is zero after the
+  // previous Montgomery step, so E >> 64 is what remains) and Y the old O; on exit X is the new O and
+  // Y the new E.
+  static PB_HD void mul_row(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t bi) {
+    constexpr bool S0 = (PB_SPLIT & 1) != 0, S1 = (PB_SPLIT & 2) != 0;
+    Y[0] = add_cc(Y[0], X[1]);
 #pragma unroll
-      for (int k = 0; k < N; k += 2) {
-        if (k + 2 < N)
-          link<S0, true, true>(X[k], X[k + 1], a[k + 1], bi, X[k + 2], X[k + 3]);
-        else
-          link<S0, true, false>(X[k], X[k + 1], a[k + 1], bi, 0u, 0u);
-      }
-      link<S1, false, true>(Y[0], Y[1], a[0], bi, Y[0], Y[1]);
-#pragma unroll
-      for (int j = 2; j < N; j += 2) link<S1, true, true>(Y[j], Y[j + 1], a[j], bi, Y[j], Y[j + 1]);
-      X[N - 1] = addc(X[N - 1], 0u);
+    for (int k = 0; k < N; k += 2) {
+      if (k + 2 < N)
+        link<S0, true, true>(X[k], X[k + 1], a[k + 1], bi, X[k + 2], X[k + 3]);
+      else
+        link<S0, true, false>(X[k], X[k + 1], a[k + 1], bi, 0u, 0u);
     }
+    link<S1, false, true>(Y[0], Y[1], a[0], bi, Y[0], Y[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) link<S1, true, true>(Y[j], Y[j + 1], a[j], bi, Y[j], Y[j + 1]);
+    X[N - 1] = addc(X[N - 1], 0u);
+  }
+  // A further product in the same row: T += c * di, with X = O and Y = E already in their new roles.
+  static PB_HD void acc_row(uint32_t* X, uint32_t* Y, const uint32_t* c, uint32_t di) {
+    constexpr bool S0 = (PB_SPLIT & 1) != 0, S1 = (PB_SPLIT & 2) != 0;
+    link<S0, false, true>(X[0], X[1], c[1], di, X[0], X[1]);
+#pragma unroll
+    for (int k = 2; k < N; k += 2) {
+      if (k + 2 < N)
+        link<S0, true, true>(X[k], X[k + 1], c[k + 1], di, X[k], X[k + 1]);
+      else
+        link<S0, true, false>(X[k], X[k + 1], c[k + 1], di, X[k], X[k + 1]);
+    }
+    link<S1, false, true>(Y[0], Y[1], c[0], di, Y[0], Y[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) link<S1, true, true>(Y[j], Y[j + 1], c[j], di, Y[j], Y[j + 1]);
+    X[N - 1] = addc(X[N - 1], 0u);
+  }
+  // The Montgomery step of a row: T += m * p with m chosen so that the low limb (Y[0]) vanishes.
+  static PB_HD void red_row(uint32_t* X /* O */, uint32_t* Y /* E */) {
+    constexpr bool S2 = (PB_SPLIT & 4) != 0, S3 = (PB_SPLIT & 8) != 0;
     const uint32_t m = mul_lo(Y[0], P::inv());
 #pragma unroll
     for (int k = 0; k < N; k += 2) {
@@ -249,6 +268,12 @@ struct Field {
 #pragma unroll
     for (int j = 2; j < N; j += 2) link<S3, true, true>(Y[j], Y[j + 1], P::MOD(j), m, Y[j], Y[j + 1]);
     X[N - 1] = addc(X[N - 1], 0u);
+  }
+  template <bool FIRST>
+  static PB_HD void mont_row(uint32_t* X /* old E -> new O */, uint32_t* Y /* old O -> new E */,
+                             const uint32_t* a, uint32_t bi) {
+    if (!FIRST) mul_row(X, Y, a, bi);
+    red_row(X, Y);
   }
 
   friend PB_HD Field operator*(const Field& a, const Field& b) {
@@ -278,6 +303,46 @@ struct Field {
     return r;
   }
   PB_HD Field sqr() const { return (*this) * (*this); }
+
+  // a*b + c*d with ONE Montgomery reduction: each row accumulates both partial products before its
+  // Montgomery step (3N^2 multiply-adds instead of 4N^2).  Only for moduli with at least two spare
+  // bits in the top limb (Fp: 381 of 384 bits), where the running sum keeps fitting the two
+  // accumulators and the result stays below 2p; Fr (255 of 256 bits) must not use it.
+  static PB_HD Field mul2(const Field& a, const Field& b, const Field& c, const Field& d) {
+    static_assert((P::MOD(N - 1) >> 30) == 0, "mul2 needs two spare bits in the top limb of the modulus");
+    uint32_t A[N], B[N];
+    {
+      const uint32_t bi = b.v[0];
+#pragma unroll
+      for (int j = 0; j < N; j += 2) {
+        mul_pair(A[j], A[j + 1], a.v[j], bi);
+        mul_pair(B[j], B[j + 1], a.v[j + 1], bi);
+      }
+      acc_row(B, A, c.v, d.v[0]);
+      red_row(B, A);  // E = A, O = B
+    }
+#pragma unroll
+    for (int i = 1; i < N; i += 2) {
+      mul_row(A, B, a.v, b.v[i]);
+      acc_row(A, B, c.v, d.v[i]);
+      red_row(A, B);  // E = B, O = A
+      if (i + 1 < N) {
+        mul_row(B, A, a.v, b.v[i + 1]);
+        acc_row(B, A, c.v, d.v[i + 1]);
+        red_row(B, A);  // E = A, O = B
+      }
+    }
+    uint32_t t[N];
+    t[0] = add_cc(A[0], B[1]);
+#pragma unroll
+    for (int k = 1; k < N - 1; k++) t[k] = addc_cc(A[k], B[k + 1]);
+    t[N - 1] = addc(A[N - 1], 0u);
+    Field r;
+    final_sub(r.v, t, 0u);
+    return r;
+  }
+  // a*b - c*d
+  static PB_HD Field mul_sub(const Field& a, const Field& b, const Field& c, const Field& d) { return mul2(a, b, c.neg(), d); }
 
   // (Interleaving several independent products in program order was tried for instruction-level
   // parallelism and gives nothing: ptxas keeps at most ~6 carry chains in flight - there are only 7

@@ -56,7 +56,7 @@ PB_HD G1Xyzz xyzz_dbl_affine(const Fp& x1, const Fp& y1) {
   Fp xx = x1.sqr();
   Fp m = xx.dbl() + xx;
   r.x = m.sqr() - s.dbl();
-  r.y = m * (s - r.x) - w * y1;
+  r.y = Fp::mul_sub(m, s - r.x, w, y1);  // two products, one reduction
   r.zz = v;
   r.zzz = w;
   return r;
@@ -74,7 +74,7 @@ PB_HD G1Xyzz xyzz_dbl(const G1Xyzz& p) {
   Fp xx = p.x.sqr();
   Fp m = xx.dbl() + xx;
   r.x = m.sqr() - s.dbl();
-  r.y = m * (s - r.x) - w * p.y;
+  r.y = Fp::mul_sub(m, s - r.x, w, p.y);
   r.zz = v * p.zz;
   r.zzz = w * p.zzz;
   return r;
@@ -105,7 +105,7 @@ PB_HD void xyzz_madd(G1Xyzz& acc, const Fp& x2, const Fp& y2) {
   Fp ppp = p * pp;
   Fp q = acc.x * pp;
   Fp x3 = r.sqr() - ppp - q.dbl();
-  Fp y3 = r * (q - x3) - acc.y * ppp;
+  Fp y3 = Fp::mul_sub(r, q - x3, acc.y, ppp);
   acc.x = x3;
   acc.y = y3;
   acc.zz = acc.zz * pp;
@@ -136,7 +136,7 @@ PB_HD void xyzz_add(G1Xyzz& acc, const G1Xyzz& o) {
   Fp ppp = p * pp;
   Fp q = u1 * pp;
   Fp x3 = r.sqr() - ppp - q.dbl();
-  Fp y3 = r * (q - x3) - s1 * ppp;
+  Fp y3 = Fp::mul_sub(r, q - x3, s1, ppp);
   acc.x = x3;
   acc.y = y3;
   acc.zz = acc.zz * o.zz * pp;

@@ -49,6 +49,20 @@ int ht_fp_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t
   return 0;
 }
 
+// out = a*b + c*d (sub = 0) or a*b - c*d (sub = 1), one Montgomery reduction (Field::mul2)
+int ht_fp_mul2(int sub, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, uint32_t* out, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    Fp x, y, z, w;
+    memcpy(x.v, a + 12 * i, 48);
+    memcpy(y.v, b + 12 * i, 48);
+    memcpy(z.v, c + 12 * i, 48);
+    memcpy(w.v, d + 12 * i, 48);
+    const Fp r = sub ? Fp::mul_sub(x, y, z, w) : Fp::mul2(x, y, z, w);
+    memcpy(out + 12 * i, r.v, 48);
+  }
+  return 0;
+}
+
 // Sum of n affine points (raw 96-byte layout) through xyzz_madd, with signs (1 = negate);
 // then chain-adds the partial sums pairwise through xyzz_add to also exercise the full adder.
 int ht_g1_sum(const uint32_t* pts, const uint8_t* neg, size_t n, uint32_t* out_affine) {

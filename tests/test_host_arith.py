@@ -56,6 +56,24 @@ def test_field_ops(ht, name, mod, nbytes):
     assert got == [(pow(x, -1, mod) * Rm % mod) if x else 0 for x in small]
 
 
+def test_fp_two_products_one_reduction(ht):
+    """Field::mul2 / mul_sub (a*b +- c*d with a single Montgomery reduction), including operands at
+    the top of the range, where the running sum is largest."""
+    mod, nb = R.P_MOD, 48
+    rng = random.Random(4321)
+    vals = _edge(mod) + [rng.randrange(mod) for _ in range(200)]
+    quads = [(mod - 1,) * 4, (mod - 1, mod - 1, 0, 5), (0, 0, mod - 1, mod - 1), (mod - 1, mod - 2, mod - 1, 1)]
+    quads += [tuple(rng.choice(vals) for _ in range(4)) for _ in range(2000)]
+    Rinv = pow(1 << 384, -1, mod)
+    cols = [b"".join(q[k].to_bytes(nb, "little") for q in quads) for k in range(4)]
+    for sub in (0, 1):
+        out = ctypes.create_string_buffer(len(quads) * nb)
+        assert ht.ht_fp_mul2(sub, *cols, out, ctypes.c_size_t(len(quads))) == 0
+        got = [int.from_bytes(out.raw[i * nb : (i + 1) * nb], "little") for i in range(len(quads))]
+        sign = -1 if sub else 1
+        assert got == [(a * b + sign * c * d) * Rinv % mod for a, b, c, d in quads]
+
+
 def test_g1_sum_and_mul(ht):
     rng = random.Random(99)
     g = R.G1_GEN
