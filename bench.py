@@ -33,9 +33,10 @@ N_GATES = (1 << LOG_GATES) - 6          # fills the 2^16 domain, commit key trim
 SRS_POINTS = (1 << LOG_GATES) + 7
 SRS_X, SRS_G = 0x1234567, 0x7654321     # synthetic "toxic waste" (seeded; a real SRS comes from a ceremony)
 LABEL = b"bench-2^16"
-# per G1 mixed addition (XYZZ madd = 8M + 2S in Fp) the SASS of k_msm_accumulate issues 8 x 276 IMAD.WIDE for the
-# single products and 420 for the fused pair R(Q - X3) - Y1 PPP (two products, one Montgomery reduction)
-IMAD_PER_ADD = 8 * 276 + 420
+# per G1 mixed addition (XYZZ madd = 8M + 2S in Fp) the SASS of k_msm_accumulate issues 276 IMAD.WIDE per product,
+# 210 per squaring (symmetric partial products once) and 420 for the fused pair R(Q - X3) - Y1 PPP (two products,
+# one Montgomery reduction): 6 products + 2 squarings + 1 fused pair
+IMAD_PER_ADD = 6 * 276 + 2 * 210 + 420
 FP_PRODUCTS_PER_ADD = IMAD_PER_ADD / 276.0  # in units of one carry-chained Fp product
 IMAD_PER_BUTTERFLY = 137
 
@@ -229,7 +230,7 @@ def run_ours(args):
                 "carry_chain_ceiling": {"fp_products_per_s": 30.3e9, "adds_per_s": 30.3e9 / FP_PRODUCTS_PER_ADD,
                                         "frac": adds_per_s * FP_PRODUCTS_PER_ADD / 30.3e9,
                                         "source": "tools/mulbench on this pool's B200: IMAD.WIDE.U32.X (carry in/out) issues at half the "
-                                                  "rate of carry-free IMAD.WIDE; 9.5 Fp-product equivalents per mixed addition"},
+                                                  "rate of carry-free IMAD.WIDE; 9.0 Fp-product equivalents per mixed addition"},
                 "note": "both hot kernels are IMAD-pipe bound at 256/381-bit precision; HBM fraction is reported because the contract asks for it"},
     }
     ntt = ntt_microbench(L, torch, imad.value)

@@ -302,7 +302,86 @@ struct Field {
     final_sub(r.v, t, 0u);
     return r;
   }
-  PB_HD Field sqr() const { return (*this) * (*this); }
+  // Squaring with the symmetric partial products taken once: a^2 = sum_i a_i * B_i with
+  // B_i = a_i 2^(32i) + 2 sum_{k>i} a_k 2^(32k), so row i multiplies a_i only by the limbs k >= i of
+  // the doubled operand (N(N+1)/2 multiply-adds instead of N^2; the Montgomery steps are unchanged).
+  // The skipped links of the shifting accumulator become plain carry-propagating adds.
+  // Row 0 adds a_0 * 2a at once, twice what a row of the ordinary product adds, so the running sum
+  // needs 3p * 2^32 < 2^(32(N+1)): two spare bits in the top limb.  Fp has three; Fr (one) keeps the
+  // ordinary product.
+  template <int I>
+  static PB_HD uint32_t sq_limb(const uint32_t* a, const uint32_t* a2, int k) {
+    return k == I ? a[k] : (k == I + 1 ? (a[k] << 1) : a2[k]);
+  }
+  template <int I>
+  static PB_HD void sqr_row(uint32_t* X, uint32_t* Y, const uint32_t* a, const uint32_t* a2) {
+    constexpr bool S0 = (PB_SPLIT & 1) != 0, S1 = (PB_SPLIT & 2) != 0;
+    const uint32_t bi = a[I];
+    Y[0] = add_cc(Y[0], X[1]);
+#pragma unroll
+    for (int k = 0; k < N; k += 2) {
+      if (k + 1 < I) {  // no product at this limb: shift and propagate the carry
+        X[k] = addc_cc(X[k + 2], 0u);
+        X[k + 1] = addc_cc(X[k + 3], 0u);
+      } else if (k + 2 < N) {
+        link<S0, true, true>(X[k], X[k + 1], sq_limb<I>(a, a2, k + 1), bi, X[k + 2], X[k + 3]);
+      } else {
+        link<S0, true, false>(X[k], X[k + 1], sq_limb<I>(a, a2, k + 1), bi, 0u, 0u);
+      }
+    }
+    constexpr int J0 = (I + 1) & ~1;  // first even limb >= I
+    if (J0 < N) {
+      link<S1, false, true>(Y[J0], Y[J0 + 1], sq_limb<I>(a, a2, J0), bi, Y[J0], Y[J0 + 1]);
+#pragma unroll
+      for (int j = J0 + 2; j < N; j += 2) link<S1, true, true>(Y[j], Y[j + 1], sq_limb<I>(a, a2, j), bi, Y[j], Y[j + 1]);
+      X[N - 1] = addc(X[N - 1], 0u);
+    }
+  }
+  template <int I>
+  static PB_HD void sqr_rows(uint32_t* A, uint32_t* B, const uint32_t* a, const uint32_t* a2) {
+    if constexpr (I < N) {
+      sqr_row<I>(A, B, a, a2);  // E = B, O = A
+      red_row(A, B);
+      if constexpr (I + 1 < N) {
+        sqr_row<I + 1>(B, A, a, a2);  // E = A, O = B
+        red_row(B, A);
+      }
+      sqr_rows<I + 2>(A, B, a, a2);
+    }
+  }
+  PB_HD Field sqr() const {
+    if constexpr ((P::MOD(N - 1) >> 30) != 0) {
+      return (*this) * (*this);
+    } else {
+      return sqr_half();
+    }
+  }
+  PB_HD Field sqr_half() const {
+    static_assert((P::MOD(N - 1) >> 30) == 0, "needs two spare bits in the top limb of the modulus");
+    uint32_t a2[N];
+    a2[0] = v[0] << 1;
+#pragma unroll
+    for (int k = 1; k < N; k++) a2[k] = (v[k] << 1) | (v[k - 1] >> 31);
+    uint32_t A[N], B[N];
+    {
+      const uint32_t bi = v[0];
+#pragma unroll
+      for (int j = 0; j < N; j += 2) {
+        mul_pair(A[j], A[j + 1], sq_limb<0>(v, a2, j), bi);
+        mul_pair(B[j], B[j + 1], sq_limb<0>(v, a2, j + 1), bi);
+      }
+      red_row(B, A);  // E = A, O = B
+    }
+    sqr_rows<1>(A, B, v, a2);
+    uint32_t t[N];
+    t[0] = add_cc(A[0], B[1]);
+#pragma unroll
+    for (int k = 1; k < N - 1; k++) t[k] = addc_cc(A[k], B[k + 1]);
+    t[N - 1] = addc(A[N - 1], 0u);
+    Field r;
+    final_sub(r.v, t, 0u);
+    return r;
+  }
 
   // a*b + c*d with ONE Montgomery reduction: each row accumulates both partial products before its
   // Montgomery step (3N^2 multiply-adds instead of 4N^2).  Only for moduli with at least two spare

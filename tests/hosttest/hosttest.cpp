@@ -23,6 +23,7 @@ int ht_fr_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t
       case 3: r = x.inv(); break;
       case 4: r = x.to_mont(); break;
       case 5: r = x.from_mont(); break;
+      case 6: r = x.sqr(); break;
       default: return -1;
     }
     memcpy(out + 8 * i, r.v, 32);
@@ -42,6 +43,7 @@ int ht_fp_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t
       case 3: r = x.inv(); break;
       case 4: r = x.to_mont(); break;
       case 5: r = x.from_mont(); break;
+      case 6: r = x.sqr(); break;
       default: return -1;
     }
     memcpy(out + 12 * i, r.v, 48);

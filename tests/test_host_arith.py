@@ -50,6 +50,10 @@ def test_field_ops(ht, name, mod, nbytes):
     assert _run(fn, 2, a, b, nbytes) == [(x - y) % mod for x, y in zip(a, b)]
     assert _run(fn, 4, a, None, nbytes) == [x * Rm % mod for x in a]
     assert _run(fn, 5, a, None, nbytes) == [x * Rinv % mod for x in a]
+    sq = vals + [mod - 1 - k for k in range(40)] + [(1 << (8 * nbytes - 1)) % mod, ((1 << 31) - 1) * ((1 << (8 * nbytes)) // ((1 << 32) - 1)) % mod]
+    top = mod >> (8 * nbytes - 32)  # top limb of the modulus: largest operands with every lower limb saturated
+    sq += [((top - k) << (8 * nbytes - 32)) | ((1 << (8 * nbytes - 32)) - 1) for k in (1, 2)] + [rng.randrange(mod) for _ in range(2000)]
+    assert _run(fn, 6, sq, None, nbytes) == [x * x * Rinv % mod for x in sq]  # dedicated squaring (half the partial products)
     small = vals[:40]
     # inverse in Montgomery form: inv(aR) = a^-1 R
     got = _run(fn, 3, [x * Rm % mod for x in small], None, nbytes)
