@@ -3,8 +3,8 @@
 set -e
 cd "$(dirname "$0")"
 SRC=plonk_b200/csrc
-OUT=plonk_b200/libplonk_b200.so
-OBJ=build/obj
+OUT=${PB200_OUT:-plonk_b200/libplonk_b200.so}
+OBJ=${PB200_OBJ:-build/obj}
 mkdir -p $OBJ
 NVFLAGS="-std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xcompiler -O2 $*"
 pids=()

@@ -159,6 +159,10 @@ int pb200_imad_peak(double* mads_per_sec);
 /* Elementwise Fr / Fp Montgomery products on the device (kernel self-test of the arithmetic). */
 int pb200_selftest_fr_mul(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
 int pb200_selftest_fp_mul(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
+/* The three Fp product forms the G1 formulas use: out[0..n) = a*b, out[n..2n) = a^2,
+   out[2n..3n) = a*b - c*d (6 x u64 Montgomery limbs each). */
+int pb200_selftest_fp_ops(const uint64_t* a, const uint64_t* b, const uint64_t* c, const uint64_t* d,
+                          uint64_t* out, size_t n);
 
 #ifdef __cplusplus
 }

@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libplonk_b200.so")
+# PB200_LIB selects another build of the same library (A/B measurements of compile-time variants)
+LIB_PATH = os.environ.get("PB200_LIB") or os.path.join(_HERE, "libplonk_b200.so")
 
 PB200_OK = 0
 PB200_ERR_CUDA = -1
@@ -28,7 +29,7 @@ EXPORTS = [
     "pb200_g1_compress", "pb200_g1_decompress", "pb200_g1_add_affine", "pb200_srs_setup_from_secret",
     "pb200_profile_enable", "pb200_profile_read",
     "pb200_prover_new", "pb200_prover_free", "pb200_prover_commitments", "pb200_prove", "pb200_prove_dev",
-    "pb200_imad_peak", "pb200_selftest_fr_mul", "pb200_selftest_fp_mul",
+    "pb200_imad_peak", "pb200_selftest_fr_mul", "pb200_selftest_fp_mul", "pb200_selftest_fp_ops",
 ]
 
 

@@ -123,6 +123,49 @@ inline void mad_pair_split(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, u
 #endif
 
 // ---------------------------------------------------------------------------------------------
+// Double-precision helpers for the two-pipe ("hybrid") Montgomery product, see Field::redc48.
+// Host builds emulate fma_rz with fma() under fesetround(FE_TOWARDZERO) (tools/mulbench's check).
+// ---------------------------------------------------------------------------------------------
+#ifndef PB_FP_HYBRID
+#define PB_FP_HYBRID 0
+#endif
+#ifndef PB_FR_HYBRID
+#define PB_FR_HYBRID 0
+#endif
+}  // namespace pb
+#if !defined(__CUDA_ARCH__)
+#include <math.h>
+#include <string.h>
+#endif
+namespace pb {
+PB_HD double fma_rz(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+  return __fma_rz(a, b, c);
+#else
+  return fma(a, b, c);  // the caller has set FE_TOWARDZERO
+#endif
+}
+PB_HD uint64_t dbl_bits(double x) {
+#if defined(__CUDA_ARCH__)
+  return (uint64_t)__double_as_longlong(x);
+#else
+  uint64_t r;
+  memcpy(&r, &x, 8);
+  return r;
+#endif
+}
+PB_HD double bits_dbl(uint32_t hi, uint32_t lo) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double((int)hi, (int)lo);
+#else
+  const uint64_t r = ((uint64_t)hi << 32) | lo;
+  double x;
+  memcpy(&x, &r, 8);
+  return x;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
 // Field<P>: P supplies N (even), MOD(i), inv() (= -MOD^-1 mod 2^32), R1 (=2^(32N) mod p), R2.
 // Values are always kept fully reduced in [0, p), Montgomery form unless stated otherwise.
 // ---------------------------------------------------------------------------------------------
@@ -277,6 +320,12 @@ struct Field {
   }
 
   friend PB_HD Field operator*(const Field& a, const Field& b) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (P::HYBRID) return mul_hybrid(a, b);
+#endif
+    return mul_imad(a, b);
+  }
+  static PB_HD Field mul_imad(const Field& a, const Field& b) {
     uint32_t A[N], B[N];
     {
       const uint32_t bi = b.v[0];
@@ -350,6 +399,9 @@ struct Field {
     }
   }
   PB_HD Field sqr() const {
+#if defined(__CUDA_ARCH__)
+    if constexpr (P::HYBRID && (P::MOD(N - 1) >> 30) == 0) return sqr_hybrid();
+#endif
     if constexpr ((P::MOD(N - 1) >> 30) != 0) {
       return (*this) * (*this);
     } else {
@@ -388,6 +440,12 @@ struct Field {
   // bits in the top limb (Fp: 381 of 384 bits), where the running sum keeps fitting the two
   // accumulators and the result stays below 2p; Fr (255 of 256 bits) must not use it.
   static PB_HD Field mul2(const Field& a, const Field& b, const Field& c, const Field& d) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (P::HYBRID) return mul2_hybrid(a, b, c, d);
+#endif
+    return mul2_imad(a, b, c, d);
+  }
+  static PB_HD Field mul2_imad(const Field& a, const Field& b, const Field& c, const Field& d) {
     static_assert((P::MOD(N - 1) >> 30) == 0, "mul2 needs two spare bits in the top limb of the modulus");
     uint32_t A[N], B[N];
     {
@@ -420,6 +478,179 @@ struct Field {
     final_sub(r.v, t, 0u);
     return r;
   }
+  // -------------------------------------------------------------------------------------------
+  // Two-pipe ("hybrid") product (Fp: 384 bits = 8 x 48; Fr: 256 bits = 5 x 48 + 16).
+  //
+  // IMAD.WIDE.U32.X (carry in/out) issues at half the rate of the carry-free form, and the FP64
+  // pipe of the B200 idles next to it.  So the 2N-limb product a*b stays on the integer multiply
+  // pipe (the same rows as above without their Montgomery steps), and the Montgomery reduction - half
+  // of the multiply-adds - moves to DFMA on 48-bit limbs: m * p_j is split exactly into two 48-bit
+  // halves by
+  //     hi = fma_rz(m, p_j, 2^100)                bits(hi) = bits(2^100) + floor(m p_j / 2^48)
+  //     lo = fma_rz(m, p_j, (2^100 + 2^52) - hi)  bits(lo) = bits(2^52)  + (m p_j mod 2^48)
+  // and the raw bit patterns are summed into 64-bit integer columns by IADD3 on the ALU pipe.  Both
+  // pattern offsets are multiples of 2^48: the low 48 bits of a column are right at all times and
+  // the offsets are only taken out where a carry leaves a column.  R stays 2^(32N), so the values
+  // are the same Montgomery residues as everywhere else: when 48 does not divide 32N the last step
+  // clears only the remaining 32N mod 48 bits and the result is read from the middle of a column.
+  // m * p_j < 2^96 and a column sums at most 17 terms below 2^48 plus a carry, far inside 64 bits.
+  // -------------------------------------------------------------------------------------------
+  static constexpr int L48 = (32 * N + 47) / 48;       // 48-bit limbs of the modulus (Fp 8, Fr 6)
+  static constexpr int CUT_COL = (32 * N) / 48;        // the column that holds bit 32N ...
+  static constexpr int CUT_SH = (32 * N) % 48;         // ... at this bit (Fp: 8, 0; Fr: 5, 16)
+  static constexpr int LAST_BITS = 32 * N - 48 * (L48 - 1);  // width of the last reduction step (Fp 48, Fr 16)
+  static PB_HD constexpr int npairs48(int k) { return k < 0 ? 0 : (k < L48 ? k + 1 : (k <= 2 * L48 - 2 ? 2 * L48 - 1 - k : 0)); }
+  // what the L48^2 dual products have put into column k by the time it is read (mod 2^64)
+  static PB_HD constexpr uint64_t col_off48(int k) {
+    return (uint64_t)npairs48(k) * 0x4330000000000000ull + (uint64_t)npairs48(k - 1) * 0x4630000000000000ull;
+  }
+  static PB_HD uint32_t word_or_zero(const uint32_t* T, int k) { return k < 2 * N ? T[k] : 0u; }
+  // T[2N] * 2^(-32N) mod p for T < p * 2^(32N), fully reduced.
+  static PB_HD Field redc48(const uint32_t* T) {
+    uint64_t c[2 * L48];
+    // T[2N-1] has at least two spare bits, so `gate` is zero - but ptxas cannot know, which keeps it
+    // from starting the reduction (whose 64-bit adds want carry predicates) inside the carry chains
+    // of the product that made T; interleaved, the two spill predicates to registers.
+    const uint32_t gate = T[2 * N - 1] >> 30;
+#pragma unroll
+    for (int q = 0; q < L48; q++) {  // three 32-bit words -> two 48-bit limbs (zero beyond T)
+      const uint32_t w0 = word_or_zero(T, 3 * q) | (q == 0 ? gate : 0u), w1 = word_or_zero(T, 3 * q + 1),
+                     w2 = word_or_zero(T, 3 * q + 2);
+      c[2 * q] = (uint64_t)w0 | ((uint64_t)(w1 & 0xffffu) << 32);
+      c[2 * q + 1] = (uint64_t)((w1 >> 16) | (w2 << 16)) | ((uint64_t)(w2 >> 16) << 32);
+    }
+    const double C1 = 0x1p100, C2 = 0x1p100 + 0x1p52;
+#pragma unroll
+    for (int i = 0; i < L48; i++) {
+      // m = c[i] * (-p^-1) mod 2^48 (one IMAD.WIDE + two IMAD; mod 2^LAST_BITS in the last step),
+      // then as a double
+      const uint32_t qlo = (uint32_t)c[i], qhi = (uint32_t)(c[i] >> 32);
+      const uint64_t r = (uint64_t)qlo * P::inv48_lo();
+      uint32_t rlo = (uint32_t)r, rhi = ((uint32_t)(r >> 32) + qlo * P::inv48_hi() + qhi * P::inv48_lo()) & 0xffffu;
+      if (i == L48 - 1 && LAST_BITS < 48) {
+        static_assert(LAST_BITS == 48 || LAST_BITS <= 32, "last step narrower than a word or a whole limb");
+        rhi = 0;
+        if (LAST_BITS < 32) rlo &= (1u << (LAST_BITS & 31)) - 1u;
+      }
+      const double m = bits_dbl(0x43300000u | rhi, rlo) - 0x1p52;
+      double hi_prev = 0;
+#pragma unroll
+      for (int j = 0; j < L48; j++) {
+        const double pj = (double)P::MOD48(j);
+        const double hi = fma_rz(m, pj, C1);
+        const double lo = fma_rz(m, pj, C2 - hi);
+        if (j == 0)
+          c[i] += dbl_bits(lo);
+        else
+          c[i + j] += dbl_bits(lo) + dbl_bits(hi_prev);
+        hi_prev = hi;
+      }
+      c[i + L48] += dbl_bits(hi_prev);
+      // a column wholly below bit 32N is complete now and is 0 mod 2^48: what is above bit 48 moves
+      // to the next column
+      if (i < CUT_COL) c[i + 1] += (c[i] - col_off48(i)) >> 48;
+    }
+    // the result starts at bit CUT_SH of column CUT_COL: offsets out, carries through, 32-bit words
+#pragma unroll
+    for (int k = CUT_COL; k < 2 * L48; k++) c[k] -= col_off48(k);
+#pragma unroll
+    for (int k = CUT_COL; k < 2 * L48 - 1; k++) {
+      c[k + 1] += c[k] >> 48;
+      c[k] &= 0xffffffffffffull;
+    }
+    uint32_t t[N];
+#pragma unroll
+    for (int w = 0; w < N; w++) {
+      const int s = CUT_SH + 32 * w, k = CUT_COL + s / 48, o = s % 48;  // o is 0, 16 or 32
+      if (o == 0)
+        t[w] = (uint32_t)c[k];
+      else if (o == 16)
+        t[w] = (uint32_t)(c[k] >> 16);
+      else
+        t[w] = (uint32_t)(c[k] >> 32) | ((uint32_t)c[k + 1] << 16);
+    }
+    Field res;
+    final_sub(res.v, t, 0u);
+    return res;
+  }
+  // E = B (low word already out), O = A after the last row: upper half T[N..2N) = A + (B >> 32)
+  static PB_HD void wide_top(uint32_t* T, const uint32_t* A, const uint32_t* B) {
+    T[N] = add_cc(A[0], B[1]);
+#pragma unroll
+    for (int k = 1; k < N - 1; k++) T[N + k] = addc_cc(A[k], B[k + 1]);
+    T[2 * N - 1] = addc(A[N - 1], 0u);
+  }
+  // T[2N] = a*b (+ c*d): the rows of the Montgomery product without their reduction steps; the low
+  // word of the running sum leaves as an output word after every row.
+  template <bool TWO>
+  static PB_HD void wide_mul(uint32_t* T, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d) {
+    uint32_t A[N], B[N];
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      mul_pair(A[j], A[j + 1], a[j], b[0]);
+      mul_pair(B[j], B[j + 1], a[j + 1], b[0]);
+    }
+    if (TWO) acc_row(B, A, c, d[0]);
+    T[0] = A[0];  // E = A, O = B
+#pragma unroll
+    for (int i = 1; i < N; i += 2) {
+      mul_row(A, B, a, b[i]);  // E = B, O = A
+      if (TWO) acc_row(A, B, c, d[i]);
+      T[i] = B[0];
+      if (i + 1 < N) {
+        mul_row(B, A, a, b[i + 1]);  // E = A, O = B
+        if (TWO) acc_row(B, A, c, d[i + 1]);
+        T[i + 1] = A[0];
+      }
+    }
+    wide_top(T, A, B);
+  }
+  template <int I>
+  static PB_HD void wide_sqr_rows(uint32_t* T, uint32_t* A, uint32_t* B, const uint32_t* a, const uint32_t* a2) {
+    if constexpr (I < N) {
+      sqr_row<I>(A, B, a, a2);  // E = B, O = A
+      T[I] = B[0];
+      if constexpr (I + 1 < N) {
+        sqr_row<I + 1>(B, A, a, a2);  // E = A, O = B
+        T[I + 1] = A[0];
+      }
+      wide_sqr_rows<I + 2>(T, A, B, a, a2);
+    }
+  }
+  static PB_HD void wide_sqr(uint32_t* T, const uint32_t* v) {
+    uint32_t a2[N];
+    a2[0] = v[0] << 1;
+#pragma unroll
+    for (int k = 1; k < N; k++) a2[k] = (v[k] << 1) | (v[k - 1] >> 31);
+    uint32_t A[N], B[N];
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      mul_pair(A[j], A[j + 1], sq_limb<0>(v, a2, j), v[0]);
+      mul_pair(B[j], B[j + 1], sq_limb<0>(v, a2, j + 1), v[0]);
+    }
+    T[0] = A[0];
+    wide_sqr_rows<1>(T, A, B, v, a2);
+    wide_top(T, A, B);
+  }
+  static PB_HD Field mul_hybrid(const Field& a, const Field& b) {
+    uint32_t T[2 * N];
+    wide_mul<false>(T, a.v, b.v, a.v, b.v);
+    return redc48(T);
+  }
+  PB_HD Field sqr_hybrid() const {
+    static_assert((P::MOD(N - 1) >> 30) == 0, "needs two spare bits in the top limb of the modulus");
+    uint32_t T[2 * N];
+    wide_sqr(T, v);
+    return redc48(T);
+  }
+  // a*b + c*d < 2p^2 < p * 2^(32N) needs one spare bit
+  static PB_HD Field mul2_hybrid(const Field& a, const Field& b, const Field& c, const Field& d) {
+    static_assert((P::MOD(N - 1) >> 30) == 0, "needs two spare bits in the top limb of the modulus");
+    uint32_t T[2 * N];
+    wide_mul<true>(T, a.v, b.v, c.v, d.v);
+    return redc48(T);
+  }
+
   // a*b - c*d
   static PB_HD Field mul_sub(const Field& a, const Field& b, const Field& c, const Field& d) { return mul2(a, b, c.neg(), d); }
 
@@ -481,6 +712,15 @@ static __constant__ uint32_t c_fr_inv = 0xffffffffu;
 
 struct FrParams {
   static constexpr int N = 8;
+  static constexpr bool HYBRID = PB_FR_HYBRID != 0;
+  // r in 48-bit limbs and -r^-1 mod 2^48, for Field::redc48
+  static PB_HD constexpr uint64_t MOD48(int j) {
+    constexpr uint64_t T[6] = {0xffff00000001ull, 0xfffe5bfeffffull, 0xd80553bda402ull, 0x3339d80809a1ull,
+                               0xa753299d7d48ull, 0x73edull};
+    return T[j];
+  }
+  static PB_HD constexpr uint32_t inv48_lo() { return 0xffffffffu; }
+  static PB_HD constexpr uint32_t inv48_hi() { return 0xfffeu; }
   static PB_HD uint32_t inv() {
 #if defined(__CUDA_ARCH__)
     return c_fr_inv;
@@ -498,6 +738,15 @@ struct FrParams {
 
 struct FpParams {
   static constexpr int N = 12;
+  static constexpr bool HYBRID = PB_FP_HYBRID != 0;
+  // p in 48-bit limbs and -p^-1 mod 2^48, for Field::redc48
+  static PB_HD constexpr uint64_t MOD48(int j) {
+    constexpr uint64_t T[8] = {0xffffffffaaabull, 0xb153ffffb9feull, 0xf6241eabfffeull, 0x6730d2a0f6b0ull,
+                               0x4b84f38512bfull, 0x434bacd76477ull, 0xe69a4b1ba7b6ull, 0x1a0111ea397full};
+    return T[j];
+  }
+  static PB_HD constexpr uint32_t inv48_lo() { return 0xfffcfffdu; }
+  static PB_HD constexpr uint32_t inv48_hi() { return 0xfffcu; }
   static PB_HD uint32_t inv() { return 0xfffcfffdu; }
   PB_LIMB_TABLE(MOD, 12, 0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
                 0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau)

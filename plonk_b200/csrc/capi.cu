@@ -91,6 +91,7 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
 int srs_upload(const uint8_t* raw, size_t n_points, pb200_srs** out);
 int selftest_mul(int which, const uint64_t* a, const uint64_t* b, uint64_t* o, size_t n);
 int imad_peak(double* out);
+int selftest_fp_ops(const uint64_t* a, const uint64_t* b, const uint64_t* c, const uint64_t* d, uint64_t* o, size_t n);
 size_t srs_len(const pb200_srs* s);
 int srs_setup(const uint64_t* x_mont, const uint64_t* g_scalar_mont, size_t n, uint8_t* out_raw);
 int g1_decompress(const uint8_t* in, size_t n, int check_subgroup, uint8_t* out_raw);
@@ -328,5 +329,11 @@ int pb200_selftest_fr_mul(const uint64_t* a, const uint64_t* b, uint64_t* out, s
 int pb200_selftest_fp_mul(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
   PB_TRY(ensure_init());
   return selftest_mul(1, a, b, out, n);
+}
+int pb200_selftest_fp_ops(const uint64_t* a, const uint64_t* b, const uint64_t* c, const uint64_t* d,
+                          uint64_t* out, size_t n) {
+  PB_TRY(ensure_init());
+  if (!a || !b || !c || !d || !out) return fail(PB200_ERR_INVALID_ARG, "null argument");
+  return selftest_fp_ops(a, b, c, d, out, n);
 }
 }

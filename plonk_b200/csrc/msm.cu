@@ -552,6 +552,15 @@ __global__ void k_selftest_fp_mul(const uint4* a, const uint4* b, uint4* o, size
   st_fp(o + 3 * i, x * y);
 }
 
+__global__ void k_selftest_fp_ops(const uint4* a, const uint4* b, const uint4* c, const uint4* d, uint4* o, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp x = ld_fp(a + 3 * i), y = ld_fp(b + 3 * i), z = ld_fp(c + 3 * i), w = ld_fp(d + 3 * i);
+  st_fp(o + 3 * i, x * y);
+  st_fp(o + 3 * (n + i), x.sqr());
+  st_fp(o + 3 * (2 * n + i), Fp::mul_sub(x, y, z, w));
+}
+
 // Register-only IMAD.WIDE throughput probe: 8 independent 64-bit accumulators per thread.
 __global__ void k_imad_peak(unsigned* out, int iters, unsigned seed) {
   unsigned a = threadIdx.x * 2654435761u + seed, b = blockIdx.x * 40503u + 12345u;
@@ -680,7 +689,9 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
   }
   {
     // CTA shape: 64 threads x 4 CTAs/SM and 128 x 2 hold the same 8 warps per SM (register-limited);
-    // the smaller CTA balances the tail of the launch better when there are few waves.
+    // the smaller CTA balances the tail of the launch better when there are few waves.  Forcing 12 or
+    // 16 warps per SM (__launch_bounds__(128, 3 | 4): 168 / 128 registers, 60 / 660 bytes spilled) was
+    // measured and is slower: 142.5 / 138.1 against 147.6 proofs/s (profiles/ab_occupancy_r01).
     static const int acc_block = [] {
       const char* e = getenv("PB200_ACC_BLOCK");
       return e ? atoi(e) : 128;
@@ -867,6 +878,26 @@ int selftest_mul(int which, const uint64_t* a, const uint64_t* b, uint64_t* o, s
   PB_CUDA(cudaMemcpyAsync(o, dout, bytes, cudaMemcpyDeviceToHost, st));
   PB_CUDA(cudaStreamSynchronize(st));
   cudaFree(da); cudaFree(db); cudaFree(dout);
+  return 0;
+}
+
+int selftest_fp_ops(const uint64_t* a, const uint64_t* b, const uint64_t* c, const uint64_t* d, uint64_t* o, size_t n) {
+  cudaStream_t st = thread_stream();
+  const size_t bytes = n * 48;
+  uint4* buf;  // a | b | c | d | three outputs
+  PB_CUDA(cudaMalloc((void**)&buf, 7 * bytes));
+  const uint64_t* in[4] = {a, b, c, d};
+  for (int k = 0; k < 4; k++) {
+    cudaError_t e = cudaMemcpyAsync((char*)buf + k * bytes, in[k], bytes, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { cudaFree(buf); PB_CUDA(e); }
+  }
+  uint4* p = buf;
+  const size_t q = bytes / 16;
+  if (n) PB_LAUNCH(k_selftest_fp_ops, div_up(n, 128), 128, 0, st, p, p + q, p + 2 * q, p + 3 * q, p + 4 * q, n);
+  cudaError_t e = cudaMemcpyAsync(o, (char*)buf + 4 * bytes, 3 * bytes, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(buf);
+  PB_CUDA(e);
   return 0;
 }
 

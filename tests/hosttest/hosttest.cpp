@@ -1,6 +1,7 @@
 // Host build (g++) of the device arithmetic headers, for CPU-side validation of the multi-limb
 // algorithms against the Python oracle.  TEST INFRASTRUCTURE: the PTX carry chains are emulated by
 // bigint.cuh's host primitives; nothing here is reachable from the product library.
+#include <fenv.h>
 #include <stddef.h>
 #include <string.h>
 
@@ -62,6 +63,41 @@ int ht_fp_mul2(int sub, const uint32_t* a, const uint32_t* b, const uint32_t* c,
     const Fp r = sub ? Fp::mul_sub(x, y, z, w) : Fp::mul2(x, y, z, w);
     memcpy(out + 12 * i, r.v, 48);
   }
+  return 0;
+}
+
+// The two-pipe Fp product (Field::mul_hybrid / sqr_hybrid / mul2_hybrid: integer product + DFMA
+// Montgomery reduction).  The device rounds toward zero per instruction (DFMA.RZ); the host emulation
+// needs the rounding mode set around the calls (and -frounding-math -mfma when compiling).
+// op: 0 a*b, 1 a^2, 2 a*b + c*d
+int ht_fp_hybrid(int op, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, uint32_t* out, size_t n) {
+  const int old = fegetround();
+  fesetround(FE_TOWARDZERO);
+  for (size_t i = 0; i < n; i++) {
+    Fp x, y, z, w, r;
+    memcpy(x.v, a + 12 * i, 48);
+    if (b) memcpy(y.v, b + 12 * i, 48);
+    if (c) memcpy(z.v, c + 12 * i, 48);
+    if (d) memcpy(w.v, d + 12 * i, 48);
+    r = op == 0 ? Fp::mul_hybrid(x, y) : (op == 1 ? x.sqr_hybrid() : Fp::mul2_hybrid(x, y, z, w));
+    memcpy(out + 12 * i, r.v, 48);
+  }
+  fesetround(old);
+  return 0;
+}
+
+// The same for Fr (a*b only: 256 = 5 x 48 + 16, the last reduction step is 16 bits wide).
+int ht_fr_hybrid(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
+  const int old = fegetround();
+  fesetround(FE_TOWARDZERO);
+  for (size_t i = 0; i < n; i++) {
+    Fr x, y;
+    memcpy(x.v, a + 8 * i, 32);
+    memcpy(y.v, b + 8 * i, 32);
+    const Fr r = Fr::mul_hybrid(x, y);
+    memcpy(out + 8 * i, r.v, 32);
+  }
+  fesetround(old);
   return 0;
 }
 

@@ -43,6 +43,31 @@ def test_device_montgomery_mul(pb, name, mod, nbytes):
     assert got == [x * y * rinv % mod for x, y in zip(a, b)]
 
 
+def test_device_fp_product_forms(pb):
+    """a*b, a^2 and a*b - c*d as ptxas compiles them for the G1 formulas (two-pipe Fp product: integer
+    product + DFMA.RZ Montgomery reduction on 48-bit limbs), incl. operands with saturated limbs."""
+    from plonk_b200._lib import check, lib
+
+    mod, nb = R.P_MOD, 48
+    rng = random.Random(11)
+    top = mod >> (8 * nb - 32)
+    edge = _edge(mod) + [mod - 1 - k for k in range(20)] + [((top - k) << (8 * nb - 32)) | ((1 << (8 * nb - 32)) - 1) for k in (1, 2)]
+    edge += [(1 << (48 * k)) % mod for k in range(1, 8)] + [((1 << (48 * k)) - 1) % mod for k in range(1, 9)]
+    vals = edge + [rng.randrange(mod) for _ in range(6000)]
+    a = vals + [rng.choice(edge) for _ in range(1000)]
+    b, c, d = ([rng.choice(vals) for _ in a] for _ in range(3))
+    b[-1000:] = [rng.choice(edge) for _ in range(1000)]
+    pack = lambda xs: b"".join(x.to_bytes(nb, "little") for x in xs)
+    n = len(a)
+    out = ctypes.create_string_buffer(3 * n * nb)
+    check(lib().pb200_selftest_fp_ops(pack(a), pack(b), pack(c), pack(d), out, ctypes.c_size_t(n)))
+    got = [int.from_bytes(out.raw[i * nb : (i + 1) * nb], "little") for i in range(3 * n)]
+    rinv = pow(1 << 384, -1, mod)
+    assert got[:n] == [x * y * rinv % mod for x, y in zip(a, b)]
+    assert got[n : 2 * n] == [x * x * rinv % mod for x in a]
+    assert got[2 * n :] == [(x * y - z * w) * rinv % mod for x, y, z, w in zip(a, b, c, d)]
+
+
 @pytest.mark.parametrize("log_n", list(range(0, 14)))
 def test_ntt_matches_oracle_all_directions(pb, log_n):
     rng = random.Random(1000 + log_n)

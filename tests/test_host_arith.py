@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def ht():
     so = os.path.join(HERE, "hosttest", "libhosttest.so")
     src = os.path.join(HERE, "hosttest", "hosttest.cpp")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, src])
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-frounding-math", "-mfma", "-shared", "-fPIC", "-o", so, src])
     return ctypes.CDLL(so)
 
 
@@ -99,6 +99,48 @@ def test_g1_sum_and_mul(ht):
     for k in (0, 1, 2, 3, 0xDEADBEEFCAFEF00D):
         assert ht.ht_g1_mul_small(R.g1_to_raw_bytes(pts[2]), ctypes.c_uint64(k), out) == 0
         assert R.g1_from_raw_bytes(out.raw) == R.g1_mul(pts[2], k)
+
+
+def test_fp_two_pipe_product(ht):
+    """Field::mul_hybrid / sqr_hybrid / mul2_hybrid (integer product + double-precision Montgomery
+    reduction on 48-bit limbs, csrc/bigint.cuh) against big-integer arithmetic."""
+    mod, nb = R.P_MOD, 48
+    rng = random.Random(4321)
+    top = mod >> (8 * nb - 32)
+    edge = _edge(mod) + [mod - 1 - k for k in range(20)] + [((top - k) << (8 * nb - 32)) | ((1 << (8 * nb - 32)) - 1) for k in (1, 2)]
+    edge += [(1 << (48 * k)) % mod for k in range(1, 8)] + [((1 << (48 * k)) - 1) % mod for k in range(1, 9)]
+    vals = edge + [rng.randrange(mod) for _ in range(3000)]
+    a = vals + [rng.choice(edge) for _ in range(500)]
+    b = [rng.choice(vals) for _ in a[: len(vals)]] + [rng.choice(edge) for _ in range(500)]
+    c = [rng.choice(vals) for _ in a]
+    d = [rng.choice(vals) for _ in a]
+    Rinv = pow(1 << 384, -1, mod)
+    pack = lambda xs: b"".join(x.to_bytes(nb, "little") for x in xs)
+    out = ctypes.create_string_buffer(len(a) * nb)
+    unpack = lambda: [int.from_bytes(out.raw[i * nb : (i + 1) * nb], "little") for i in range(len(a))]
+    assert ht.ht_fp_hybrid(0, pack(a), pack(b), None, None, out, ctypes.c_size_t(len(a))) == 0
+    assert unpack() == [x * y * Rinv % mod for x, y in zip(a, b)]
+    assert ht.ht_fp_hybrid(1, pack(a), None, None, None, out, ctypes.c_size_t(len(a))) == 0
+    assert unpack() == [x * x * Rinv % mod for x in a]
+    assert ht.ht_fp_hybrid(2, pack(a), pack(b), pack(c), pack(d), out, ctypes.c_size_t(len(a))) == 0
+    assert unpack() == [(x * y + z * w) * Rinv % mod for x, y, z, w in zip(a, b, c, d)]
+
+
+def test_fr_two_pipe_product(ht):
+    """Fr::mul_hybrid: 256 bits are five 48-bit reduction steps and one of 16 bits."""
+    mod, nb = R.R_MOD, 32
+    rng = random.Random(987)
+    edge = _edge(mod) + [mod - 1 - k for k in range(20)] + [(1 << (48 * k)) % mod for k in range(1, 6)] + [((1 << (48 * k)) - 1) % mod for k in range(1, 6)]
+    edge += [(1 << 240) - 1, ((1 << 255) - 1) % mod, (0x73ED << 240) - 1]
+    vals = edge + [rng.randrange(mod) for _ in range(4000)]
+    a = vals + [rng.choice(edge) for _ in range(500)]
+    b = [rng.choice(vals) for _ in vals] + [rng.choice(edge) for _ in range(500)]
+    pack = lambda xs: b"".join(x.to_bytes(nb, "little") for x in xs)
+    out = ctypes.create_string_buffer(len(a) * nb)
+    assert ht.ht_fr_hybrid(pack(a), pack(b), out, ctypes.c_size_t(len(a))) == 0
+    Rinv = pow(1 << 256, -1, mod)
+    got = [int.from_bytes(out.raw[i * nb : (i + 1) * nb], "little") for i in range(len(a))]
+    assert got == [x * y * Rinv % mod for x, y in zip(a, b)]
 
 
 @pytest.fixture(scope="module")

@@ -3,13 +3,69 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 #include "../../plonk_b200/csrc/bigint.cuh"
+#include "fp_dfma52.cuh"
 using namespace pb;
 
 __global__ void k_chain32(Fp* io, int iters) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   Fp a = io[i], b = io[i + 1];
-  for (int k = 0; k < iters; k++) { a = a * b; b = b * a; }
+  for (int k = 0; k < iters; k++) { a = Fp::mul_imad(a, b); b = Fp::mul_imad(b, a); }
   io[i] = a + b;
+}
+
+// IMAD product + DFMA Montgomery reduction (Field::mul_hybrid)
+__global__ void k_chainhyb(Fp* io, int iters) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  Fp a = io[i], b = io[i + 1];
+  for (int k = 0; k < iters; k++) { a = Fp::mul_hybrid(a, b); b = Fp::mul_hybrid(b, a); }
+  io[i] = a + b;
+}
+// All-FP64 product on 52-bit limbs (fp_dfma52.cuh)
+__global__ void k_chain52(pb52::F52* io, int iters) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  pb52::F52 a = io[i], b = io[i + 1];
+  for (int k = 0; k < iters; k++) { a = pb52::mul52(a, b); b = pb52::mul52(b, a); }
+#pragma unroll
+  for (int j = 0; j < 8; j++) a.l[j] += b.l[j];
+  io[i] = a;
+}
+// Pipe probes: dependent DFMA.RZ chains (8 per thread), dependent IMAD.WIDE.U32.X chains, and both
+// in the same thread, to see whether the FP64 pipe and the integer multiply pipe overlap.
+template <int MODE>  // bit 0 = DFMA, bit 1 = IMAD.WIDE.X, bit 2 = 64-bit IADD3 pairs
+__global__ void k_pipes(double* io, int iters) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double d[8];
+  uint32_t u[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) { d[k] = io[i + k]; u[k] = (uint32_t)__double_as_longlong(d[k]) | 1u; }
+  const double m = io[i + 9];
+  unsigned long long w[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) w[k] = (unsigned long long)__double_as_longlong(d[k]) * 3u;
+  for (int it = 0; it < iters; it++) {
+    if (MODE & 4) {  // 4 three-input 64-bit adds = 8 IADD3 / IADD3.X
+#pragma unroll
+      for (int k = 0; k < 4; k++) w[k] += w[(k + 1) & 3] + w[(k + 2) & 3];
+    }
+    if (MODE & 1) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) d[k] = __fma_rz(d[k], m, d[(k + 1) & 7]);
+    }
+    if (MODE & 2) {
+      pb::mad_pair<false, true>(u[0], u[1], u[6], u[7], u[0], u[1]);
+      pb::mad_pair<true, true>(u[2], u[3], u[6], u[7], u[2], u[3]);
+      pb::mad_pair<true, true>(u[4], u[5], u[0], u[7], u[4], u[5]);
+      pb::mad_pair<true, false>(u[6], u[7], u[2], u[5], u[6], u[7]);
+      pb::mad_pair<false, true>(u[0], u[1], u[4], u[7], u[0], u[1]);
+      pb::mad_pair<true, true>(u[2], u[3], u[6], u[5], u[2], u[3]);
+      pb::mad_pair<true, true>(u[4], u[5], u[2], u[7], u[4], u[5]);
+      pb::mad_pair<true, false>(u[6], u[7], u[0], u[3], u[6], u[7]);
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s += d[k] + (double)u[k] + (double)w[k & 3];
+  io[i] = s;
 }
 
 // 13 x 30-bit limbs, R = 2^390, lazy: inputs limbs < 2^30 (+eps), output carry-propagated, in [0, 2p)
@@ -127,6 +183,28 @@ int main() {
   cudaMemcpyToSymbol(P30, p30, sizeof p30);
   uint32_t pinv = 0x3ffcfffd; cudaMemcpyToSymbol(PINV30, &pinv, 4);
   const int iters = 200;
+  pb52::F52* b52; cudaMalloc(&b52, sizeof(pb52::F52) * maxthreads);
+  {  // limbs = 2^51 + small (exact integers below 2^52)
+    double* hb = (double*)malloc(sizeof(pb52::F52) * maxthreads);
+    for (size_t k = 0; k < (size_t)maxthreads * 8; k++) hb[k] = (double)((1ull << 51) + (k * 2654435761ull) % (1ull << 50));
+    cudaMemcpy(b52, hb, sizeof(pb52::F52) * maxthreads, cudaMemcpyHostToDevice); free(hb);
+  }
+  {
+    double* pd; cudaMalloc(&pd, 8 * (maxthreads + 16)); cudaMemset(pd, 0x3f, 8 * (maxthreads + 16));
+    for (int threads_per_sm : {256, 512, 1024}) {
+      int blocks = 148 * threads_per_sm / 128;
+      double ops = (double)blocks * 128 * 2000 * 8;
+      float t1 = run(k_pipes<1>, pd, blocks, 128, 2000);
+      float t2 = run(k_pipes<2>, pd, blocks, 128, 2000);
+      float t3 = run(k_pipes<3>, pd, blocks, 128, 2000);
+      float t4 = run(k_pipes<4>, pd, blocks, 128, 2000);
+      float t5 = run(k_pipes<5>, pd, blocks, 128, 2000);
+      float t6 = run(k_pipes<6>, pd, blocks, 128, 2000);
+      printf("pipes threads/SM %4d: 8 IADD3 alone %.3f ms | with 8 DFMA %.3f ms | with 8 IMAD.WIDE.X %.3f ms\n", threads_per_sm, t4, t5, t6);
+      printf("pipes threads/SM %4d: DFMA.RZ %.2f T/s | IMAD.WIDE.X %.2f T/s | both in one thread: %.2f T/s each (%.3f ms vs %.3f + %.3f)\n",
+             threads_per_sm, ops / t1 / 1e9, ops / t2 / 1e9, ops / t3 / 1e9, t3, t1, t2);
+    }
+  }
   for (int threads_per_sm : {128, 256, 384, 512, 768, 1024}) {
     int blocks = 148 * threads_per_sm / 128;
     float m32 = run(k_chain32, b32, blocks, 128, iters);
@@ -134,6 +212,10 @@ int main() {
     float m30b = run(k_chain30v2, b30, blocks, 128, iters);
     printf("   v2 30-bit: %8.3f ms (%6.2f G mul/s, %.2f us/mul/thread)\n", m30b, (double)blocks * 128 * iters * 2 / m30b / 1e6, m30b * 1e3 / (iters * 2));
     double muls = (double)blocks * 128 * iters * 2;
+    float m52 = run(k_chain52, b52, blocks, 128, iters);
+    printf("   all-FP64 52-bit limbs: %8.3f ms (%6.2f G mul/s, %.2f us/mul/thread)\n", m52, muls / m52 / 1e6, m52 * 1e3 / (iters * 2));
+    float mh = run(k_chainhyb, b32, blocks, 128, iters);
+    printf("   hybrid IMAD product + DFMA reduction: %8.3f ms (%6.2f G mul/s, %.2f us/mul/thread)\n", mh, muls / mh / 1e6, mh * 1e3 / (iters * 2));
     printf("threads/SM %4d: 32-bit carry chains %8.3f ms (%6.2f G mul/s, %.2f us/mul/thread) | 30-bit lazy %8.3f ms (%6.2f G mul/s, %.2f us/mul/thread)\n",
            threads_per_sm, m32, muls / m32 / 1e6, m32 * 1e3 / (iters * 2), m30, muls / m30 / 1e6, m30 * 1e3 / (iters * 2));
   }
