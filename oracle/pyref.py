@@ -1063,6 +1063,7 @@ def prove(pd: ProverData, rng: StdRng, comp: Composer, trace: Optional[ProofTrac
     ch["logic"] = transcript.challenge_scalar(b"logic separation challenge")
     ch["fixed"] = transcript.challenge_scalar(b"fixed base separation challenge")
     ch["var"] = transcript.challenge_scalar(b"variable base separation challenge")
+    tr.update(alpha=alpha, ch=ch)  # recorded before the quotient so that a rejected circuit still leaves them in the trace
     pi_poly = poly_trim(domain.ifft(dense_pi))
     # quotient_poly::compute (src/proof_system/quotient_poly.rs:20-137)
     n8 = 8 * size
