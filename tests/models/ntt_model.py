@@ -4,7 +4,7 @@ Pure Python over the oracle's field; used during development to validate the pas
 (tile addressing, inter-pass twiddles, digit-reversed final store) before it is transcribed to CUDA."""
 import random
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import pyref as R
 
 MOD = R.R_MOD

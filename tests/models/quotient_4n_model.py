@@ -1,6 +1,6 @@
 """Python model of a cheaper round 3: the quotient polynomial from a 4n coset instead of the 8n one.
 
-DEVELOPMENT AID (like ntt_model.py): validates, against the oracle's own quotient polynomial, the
+TEST INFRASTRUCTURE (like ntt_model.py): validates, against the oracle's own quotient polynomial, the
 algebra a CUDA implementation would use.  Not on the product path; imports oracle/ as the checker.
 
 The reference evaluates the numerator on the 8n coset g*H_8n, divides by Z_H pointwise and
@@ -22,13 +22,13 @@ misses only the top seven:
 Cost at n = 2^16: 7 transforms of 2^18 instead of 2^19 and 4n instead of 8n quotient points
 (-46 % of the Fr products of a proof) against 6 x 16 + 8 extra Horner evaluations (+10 %).
 
-Run: python tools/quotient_4n_model.py   (checks several circuits incl. every gate family and a
+Run: python tests/models/quotient_4n_model.py   (checks several circuits incl. every gate family and a
 corrupted witness; a few seconds of pure Python)."""
 import os
 import random
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import pyref as R  # noqa: E402
 
 P = R.R_MOD

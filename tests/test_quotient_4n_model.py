@@ -1,4 +1,4 @@
-"""tools/quotient_4n_model.py: the quotient polynomial recovered from a 4n coset plus eight extra
+"""tests/models/quotient_4n_model.py: the quotient polynomial recovered from a 4n coset plus eight extra
 points equals the oracle's (8n coset, src/proof_system/quotient_poly.rs:20-137), and a corrupted
 witness is rejected by both.  Design validation for the next round-3 kernel schedule."""
 import importlib.util
@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def _model():
-    spec = importlib.util.spec_from_file_location("quotient_4n_model", os.path.join(HERE, "..", "tools", "quotient_4n_model.py"))
+    spec = importlib.util.spec_from_file_location("quotient_4n_model", os.path.join(HERE, "models", "quotient_4n_model.py"))
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
     return m

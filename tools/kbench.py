@@ -56,33 +56,32 @@ for log_n, batch in [(12, 4), (16, 1), (16, 4), (19, 1), (19, 5), (20, 1), (23, 
         res[f"ntt_2^{log_n}_b{batch}_inv{inv}_coset{coset}"] = dict(ms=ms, gbutterflies_per_s=bf / ms / 1e6, gbytes_per_s=64 * n * batch / ms / 1e6)
         print(f"ntt 2^{log_n} batch {batch} inv={inv} coset={coset}: {ms:.4f} ms  {bf/ms/1e6:.2f} G butterflies/s  {64*n*batch/ms/1e6:.1f} GB/s algorithmic", flush=True)
 
-# MSM: bases = multiples of a generator-like point are not needed for timing; use the C oracle's SRS if present
-try:
-    from oracle import cref
-    for log_n in (12, 16, 18):
-        n = (1 << log_n) + 7
-        t0 = time.time()
-        srs_raw = cref.srs_from_secret(n, 12345, 6789)
-        print(f"cpu srs gen 2^{log_n}: {time.time()-t0:.1f}s", flush=True)
-        h = ctypes.c_void_p()
-        t0 = time.time()
-        check(L.pb200_srs_upload(srs_raw, n, ctypes.byref(h)))
-        print(f"srs upload+precompute 2^{log_n}: {time.time()-t0:.3f}s", flush=True)
-        for batch in (1, 4):
-            s = rand_fr_dev(n * batch)
-            out = ctypes.create_string_buffer(96 * batch)
-            f = lambda: check(L.pb200_msm_g1_dev(h, s.data_ptr(), n, batch, n, out, stream))
-            ms = time_ms(f, iters=5, warm=2)
-            L.pb200_profile_enable(1)
-            f(); f()
-            acc_ms, adds, nl, pts = ctypes.c_double(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
-            L.pb200_profile_read(ctypes.byref(acc_ms), ctypes.byref(adds), ctypes.byref(nl), ctypes.byref(pts))
-            L.pb200_profile_enable(0)
-            print(f"   accumulate kernel: {acc_ms.value/2:.3f} ms/launch, {adds.value/acc_ms.value/1e6:.3f} G adds/s", flush=True)
-            res[f"msm_2^{log_n}_b{batch}"] = dict(ms=ms, mpoints_per_s=n * batch / ms / 1e3)
-            print(f"msm 2^{log_n} batch {batch}: {ms:.3f} ms  ({n*batch/ms/1e3:.2f} M points/s)", flush=True)
-        L.pb200_srs_free(h)
-except Exception as e:  # noqa: BLE001
-    print("msm bench skipped:", e)
+# MSM: a true SRS shape (powers of a secret times a generator multiple), made on the device by the library itself
+R_MOD = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+mont = lambda v: ((v << 256) % R_MOD).to_bytes(32, "little")
+for log_n in (12, 16, 18):
+    n = (1 << log_n) + 7
+    srs_raw = ctypes.create_string_buffer(n * 96)
+    t0 = time.time()
+    check(L.pb200_srs_setup_from_secret(mont(12345), mont(6789), n, srs_raw))
+    print(f"device srs setup 2^{log_n}: {time.time()-t0:.2f}s", flush=True)
+    h = ctypes.c_void_p()
+    t0 = time.time()
+    check(L.pb200_srs_upload(srs_raw, n, ctypes.byref(h)))
+    print(f"srs upload+precompute 2^{log_n}: {time.time()-t0:.3f}s", flush=True)
+    for batch in (1, 4):
+        s = rand_fr_dev(n * batch)
+        out = ctypes.create_string_buffer(96 * batch)
+        f = lambda: check(L.pb200_msm_g1_dev(h, s.data_ptr(), n, batch, n, out, stream))
+        ms = time_ms(f, iters=5, warm=2)
+        L.pb200_profile_enable(1)
+        f(); f()
+        acc_ms, adds, nl, pts = ctypes.c_double(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        L.pb200_profile_read(ctypes.byref(acc_ms), ctypes.byref(adds), ctypes.byref(nl), ctypes.byref(pts))
+        L.pb200_profile_enable(0)
+        print(f"   accumulate kernel: {acc_ms.value/2:.3f} ms/launch, {adds.value/acc_ms.value/1e6:.3f} G adds/s", flush=True)
+        res[f"msm_2^{log_n}_b{batch}"] = dict(ms=ms, mpoints_per_s=n * batch / ms / 1e3)
+        print(f"msm 2^{log_n} batch {batch}: {ms:.3f} ms  ({n*batch/ms/1e3:.2f} M points/s)", flush=True)
+    L.pb200_srs_free(h)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/kbench.json", "w"), indent=1)
