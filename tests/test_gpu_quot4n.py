@@ -1,0 +1,26 @@
+"""Round 3 on the 4n coset (tools/patches/quot4n_prover.patch, PB200_QUOT4N=1).
+
+Skipped until the patch is applied and the library rebuilt: the variable's name is then a string in the
+library.  The switch is read once per process, so the prover parity tests (golden digest, Proof bytes ==
+CPU oracle, every gate family, the reference's BenchCircuit, CircuitUnsatisfied on a bad witness) are
+re-run in a child process with the variable set."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_prover_parity_on_the_4n_coset():
+    from plonk_b200._lib import LIB_PATH
+
+    if b"PB200_QUOT4N" not in open(LIB_PATH, "rb").read():
+        pytest.skip("tools/patches/quot4n_prover.patch is not applied in this build")
+    env = dict(os.environ, PB200_QUOT4N="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_prover.py", "tests/test_gpu_gadget_circuits.py", "-m", "gpu", "-x", "-q",
+                        "-k", "not 2_18 and not 2_20 and not cpp_mirror"], cwd=ROOT, env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
