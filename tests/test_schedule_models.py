@@ -19,3 +19,13 @@ def test_quotient_from_4n_coset_matches_reference_and_rejects_bad_witness():
     m.check(20, 1, 0)
     m.check(60, 2, 7)
     m.check(60, 4, 7, corrupt=True)
+
+
+def test_lagrange_basis_wire_commitments_equal_commit_of_blinded_polynomials():
+    """tests/models/lagrange_commit_model.py: design validation for committing to the wire polynomials
+    through their values (short scalars) instead of their coefficients."""
+    spec = importlib.util.spec_from_file_location("lagrange_commit_model", os.path.join(HERE, "models", "lagrange_commit_model.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    m.check(16, 3)
+    m.check(8, 5)
