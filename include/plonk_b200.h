@@ -154,6 +154,13 @@ int pb200_prove_dev(const pb200_prover_t* prover, const uint64_t* d_witnesses,
 int pb200_profile_enable(int on);
 int pb200_profile_read(double* accumulate_ms, uint64_t* accumulate_adds, uint64_t* accumulate_launches,
                        uint64_t* msm_points);
+/* Lagrange form of a commit key: out[j] = [L_j(x)]G = (1/n) sum_i w^(-ij) points[i] for the first
+   n = 2^k points of CommitKey::powers_of_g (reference src/commitment_scheme/kzg10/key.rs:36-41), by an
+   inverse NTT over group elements on the device.  Host buffers, n affine points of 96 bytes each (the
+   layout of pb200_srs_upload).  With it a polynomial can be committed through its evaluations on the
+   domain (sum_i p(w^i) out[i]) instead of its coefficients; the prover does not use it yet.
+   PB200_ERR_INVALID_DOMAIN unless n is a power of two. */
+int pb200_g1_lagrange_key(const uint64_t* points, size_t n, uint64_t* out);
 /* Register-only IMAD.WIDE microbenchmark: returns achieved 32x32+64 multiply-adds per second. */
 int pb200_imad_peak(double* mads_per_sec);
 /* Elementwise Fr / Fp Montgomery products on the device (kernel self-test of the arithmetic). */

@@ -26,7 +26,7 @@ EXPORTS = [
     "pb200_ntt", "pb200_ntt_dev",
     "pb200_srs_upload", "pb200_srs_free", "pb200_srs_len",
     "pb200_msm_g1", "pb200_msm_g1_dev", "pb200_msm_g1_range", "pb200_msm_g1_allgather",
-    "pb200_g1_compress", "pb200_g1_decompress", "pb200_g1_add_affine", "pb200_srs_setup_from_secret",
+    "pb200_g1_compress", "pb200_g1_decompress", "pb200_g1_add_affine", "pb200_srs_setup_from_secret", "pb200_g1_lagrange_key",
     "pb200_profile_enable", "pb200_profile_read",
     "pb200_prover_new", "pb200_prover_free", "pb200_prover_commitments", "pb200_prove", "pb200_prove_dev",
     "pb200_imad_peak", "pb200_selftest_fr_mul", "pb200_selftest_fp_mul", "pb200_selftest_fp_ops",

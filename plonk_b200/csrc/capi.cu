@@ -91,6 +91,7 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
 int srs_upload(const uint8_t* raw, size_t n_points, pb200_srs** out);
 int selftest_mul(int which, const uint64_t* a, const uint64_t* b, uint64_t* o, size_t n);
 int imad_peak(double* out);
+int lagrange_key_dev(const uint4* d_in, int log_n, uint4* d_out, cudaStream_t st);
 int selftest_fp_ops(const uint64_t* a, const uint64_t* b, const uint64_t* c, const uint64_t* d, uint64_t* o, size_t n);
 size_t srs_len(const pb200_srs* s);
 int srs_setup(const uint64_t* x_mont, const uint64_t* g_scalar_mont, size_t n, uint8_t* out_raw);
@@ -318,6 +319,25 @@ int pb200_profile_read(double* accumulate_ms, uint64_t* accumulate_adds, uint64_
   return 0;
 }
 
+int pb200_g1_lagrange_key(const uint64_t* points, size_t n, uint64_t* out) {
+  PB_TRY(ensure_init());
+  if (!points || !out) return fail(PB200_ERR_INVALID_ARG, "null argument");
+  if (n == 0 || (n & (n - 1)) != 0) return fail(PB200_ERR_INVALID_DOMAIN, "the Lagrange key needs a power-of-two size");
+  int log_n = 0;
+  while (((size_t)1 << log_n) < n) log_n++;
+  cudaStream_t st = thread_stream();
+  uint4* buf = nullptr;  // input | output
+  PB_CUDA(cudaMalloc((void**)&buf, 2 * n * 96));
+  cudaError_t e = cudaMemcpyAsync(buf, points, n * 96, cudaMemcpyHostToDevice, st);
+  int rc = 0;
+  if (e == cudaSuccess) rc = lagrange_key_dev(buf, log_n, buf + 6 * n, st);
+  if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(out, buf + 6 * n, n * 96, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && rc == 0) e = cudaStreamSynchronize(st);
+  cudaFree(buf);
+  if (rc) return rc;
+  PB_CUDA(e);
+  return 0;
+}
 int pb200_imad_peak(double* mads_per_sec) {
   PB_TRY(ensure_init());
   return imad_peak(mads_per_sec);

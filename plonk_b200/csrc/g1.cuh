@@ -143,6 +143,27 @@ PB_HD void xyzz_add(G1Xyzz& acc, const G1Xyzz& o) {
   acc.zzz = acc.zzz * o.zzz * ppp;
 }
 
+// k * P for a canonical (non-Montgomery) little-endian integer k of `words` 32-bit words: plain
+// double-and-add, variable time (public data only: twiddle factors of the group-element NTT).
+PB_HD G1Xyzz xyzz_mul(const G1Xyzz& p, const uint32_t* k, int words) {
+  G1Xyzz acc = G1Xyzz::identity();
+  bool started = false;
+  for (int w = words - 1; w >= 0; w--) {
+    for (int bit = 31; bit >= 0; bit--) {
+      if (started) acc = xyzz_dbl(acc);
+      if ((k[w] >> bit) & 1u) {
+        if (started) {
+          xyzz_add(acc, p);
+        } else {
+          acc = p;
+          started = true;
+        }
+      }
+    }
+  }
+  return acc;
+}
+
 // Affine normalisation (one inversion): x = X/ZZ, y = Y/ZZZ.
 PB_HD G1Affine xyzz_to_affine(const G1Xyzz& p) {
   G1Affine r;

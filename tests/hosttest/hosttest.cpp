@@ -5,7 +5,7 @@
 #include <stddef.h>
 #include <string.h>
 
-#include "../../plonk_b200/csrc/g1.cuh"
+#include "../../plonk_b200/csrc/ecntt.cuh"
 
 using namespace pb;
 
@@ -129,6 +129,51 @@ int ht_g1_mul_small(const uint32_t* pt, uint64_t k, uint32_t* out_affine) {
   }
   G1Affine r = xyzz_to_affine(acc);
   memcpy(out_affine, &r, 96);
+  return 0;
+}
+
+// Inverse NTT over n = 2^log_n affine G1 points (csrc/ecntt.cuh): out[j] = (1/n) sum_i w^(-ij) pts[i].
+// The stages, twiddle exponents and the bit-reversed read-out are the ones of the CUDA driver
+// (csrc/ecntt.cu); the twiddles are recomputed here from GENERATOR = 7.
+int ht_ec_intt(const uint32_t* pts, int log_n, uint32_t* out) {
+  const size_t n = (size_t)1 << log_n;
+  G1Xyzz* A = new G1Xyzz[n];
+  for (size_t i = 0; i < n; i++) {
+    G1Affine p;
+    memcpy(&p, pts + 24 * i, 96);
+    A[i] = G1Xyzz::from_affine(p);
+  }
+  // ROOT_OF_UNITY = 7^((r-1)/2^32); w_n = ROOT^(2^(32-log_n))
+  Fr seven = Fr::zero();
+  seven.v[0] = 7;
+  seven = seven.to_mont();
+  uint32_t e[8];
+  for (int i = 0; i < 8; i++) e[i] = FrParams::MOD(i);
+  e[0] -= 1;
+  uint32_t es[7];
+  for (int i = 0; i < 7; i++) es[i] = e[i + 1];  // (r - 1) >> 32
+  Fr w = seven.pow(es, 7);
+  for (int i = 0; i < 32 - log_n; i++) w = w.sqr();
+  const Fr w_inv = w.inv();
+  Fr* tw = new Fr[n / 2 + 1];
+  tw[0] = Fr::one();
+  for (size_t k = 1; k < n / 2; k++) tw[k] = tw[k - 1] * w_inv;
+  for (int s = 0; s < log_n; s++) {
+    const size_t len = n >> s, half = len >> 1;
+    for (size_t t = 0; t < n / 2; t++) {
+      const size_t blk = t / half, j = t % half, i0 = blk * len + j, ex = j << s;
+      ec_butterfly(A[i0], A[i0 + half], tw[ex], ex == 0);
+    }
+  }
+  Fr nn = Fr::zero();
+  nn.v[0] = (uint32_t)n;
+  const Fr n_inv = nn.to_mont().inv().from_mont();
+  for (size_t i = 0; i < n; i++) {
+    const G1Affine r = xyzz_to_affine(xyzz_mul(A[i], n_inv.v, 8));
+    memcpy(out + 24 * ec_bitrev((unsigned)i, log_n), &r, 96);
+  }
+  delete[] A;
+  delete[] tw;
   return 0;
 }
 }

@@ -68,6 +68,36 @@ def test_device_fp_product_forms(pb):
     assert got[2 * n :] == [(x * y - z * w) * rinv % mod for x, y, z, w in zip(a, b, c, d)]
 
 
+@pytest.mark.skipif(not __import__("os").environ.get("PB200_TEST_LAGRANGE"),
+                    reason="pb200_g1_lagrange_key was written after round 1's GPU budget was spent; its algorithm is "
+                           "validated on the host (tests/test_host_arith.py), set PB200_TEST_LAGRANGE=1 to run it on the GPU")
+def test_lagrange_key_matches_direct_sum(pb):
+    """Inverse NTT over group elements (csrc/ecntt.cu) against [L_j(x)]G = (1/n) sum_i w^(-ij) [x^i]G, and a
+    commitment through evaluations against CommitKey::commit of the interpolated polynomial."""
+    import importlib.util
+    import os
+
+    from plonk_b200._lib import check, lib
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("lagrange_commit_model", os.path.join(here, "models", "lagrange_commit_model.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    rng = random.Random(5)
+    for log_n in (0, 1, 3, 5):
+        n = 1 << log_n
+        powers = R.srs_setup(n + 8, R.StdRng.seed_from_u64(40 + log_n), keep=n)
+        out = ctypes.create_string_buffer(96 * n)
+        check(lib().pb200_g1_lagrange_key(bases_to_abi(powers), ctypes.c_size_t(n), out))
+        got = [R.g1_from_raw_bytes(out.raw[96 * j : 96 * j + 96]) for j in range(n)]
+        if log_n <= 3:
+            assert got == m.lagrange_key(powers, n)
+        vals = [rng.choice([0, 1, 3, rng.randrange(R.R_MOD)]) for _ in range(n)]
+        want = R.commit(powers, R.EvaluationDomain(n).ifft(vals))
+        assert R.jac_to_affine(R.msm_pippenger(got, vals)) == want
+    assert lib().pb200_g1_lagrange_key(bases_to_abi(powers[:3]), ctypes.c_size_t(3), out) == -2  # not a power of two
+
+
 @pytest.mark.parametrize("log_n", list(range(0, 14)))
 def test_ntt_matches_oracle_all_directions(pb, log_n):
     rng = random.Random(1000 + log_n)

@@ -143,6 +143,23 @@ def test_fr_two_pipe_product(ht):
     assert got == [x * y * Rinv % mod for x, y in zip(a, b)]
 
 
+def test_group_element_inverse_ntt_gives_the_lagrange_commit_key(ht):
+    """csrc/ecntt.cuh (butterfly, twiddle scalar multiplication, bit-reversed read-out) on the host against
+    the direct sum [L_j(x)]G = (1/n) sum_i w^(-ij) [x^i]G of tests/models/lagrange_commit_model.py."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("lagrange_commit_model", os.path.join(HERE, "models", "lagrange_commit_model.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    for log_n, seed in ((0, 1), (1, 2), (3, 3), (4, 4)):
+        n = 1 << log_n
+        powers = R.srs_setup(n + 8, R.StdRng.seed_from_u64(seed), keep=n)
+        want = m.lagrange_key(powers, n)
+        out = ctypes.create_string_buffer(96 * n)
+        assert ht.ht_ec_intt(b"".join(R.g1_to_raw_bytes(p) for p in powers[:n]), log_n, out) == 0
+        assert [R.g1_from_raw_bytes(out.raw[96 * j : 96 * j + 96]) for j in range(n)] == want
+
+
 @pytest.fixture(scope="module")
 def hp():
     so = os.path.join(HERE, "hosttest", "libhostproduct.so")
