@@ -818,6 +818,37 @@ int srs_upload(const uint8_t* raw, size_t n_points, pb200_srs** out) {
   return 0;
 }
 
+// The key's points as uploaded (window 0 of the table), n_points affine points on the device.
+const uint4* srs_points(const pb200_srs* s) { return s->table; }
+
+// srs_upload for points that are already on the device (e.g. the Lagrange form made by csrc/ecntt.cu).
+int srs_from_device(const uint4* d_points, size_t n_points, pb200_srs** out) {
+  if (n_points == 0) return fail(PB200_ERR_INVALID_ARG, "empty commit key");
+  cudaStream_t st = thread_stream();
+  pb200_srs* s = new pb200_srs();
+  s->n_points = n_points;
+  s->c = pick_window(n_points);
+  s->W = (256 + s->c - 1) / s->c;
+  s->table = nullptr;
+  cudaError_t e = cudaMalloc((void**)&s->table, (size_t)s->W * n_points * 96);
+  if (e != cudaSuccess) {
+    delete s;
+    return fail(PB200_ERR_CUDA, "cudaMalloc(commit key table)", cudaGetErrorString(e));
+  }
+  e = cudaMemcpyAsync(s->table, d_points, n_points * 96, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess) {
+    PB_LAUNCH(k_msm_precompute, div_up(n_points, 64), 64, 0, st, s->table, n_points, s->c, s->W);
+    e = cudaStreamSynchronize(st);
+  }
+  if (e != cudaSuccess) {
+    cudaFree(s->table);
+    delete s;
+    return fail(PB200_ERR_CUDA, "commit key table", cudaGetErrorString(e));
+  }
+  *out = s;
+  return 0;
+}
+
 int srs_setup(const uint64_t* x_mont, const uint64_t* g_scalar_mont, size_t n, uint8_t* out_raw) {
   cudaStream_t st = thread_stream();
   uint4* d = nullptr;
