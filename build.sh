@@ -2,7 +2,7 @@
 # Builds libplonk_b200.so (sm_100a) in-tree; translation units compile in parallel.
 set -e
 cd "$(dirname "$0")"
-SRC=plonk_b200/csrc
+SRC=${PB200_SRC:-plonk_b200/csrc}
 OUT=${PB200_OUT:-plonk_b200/libplonk_b200.so}
 OBJ=${PB200_OBJ:-build/obj}
 mkdir -p $OBJ
