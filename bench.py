@@ -9,8 +9,12 @@ A "step" is one pass of the hot path over one batch of synthetic input: `--infli
 hold independent proofs (replicas, no data-path collective), so scaling is
 weak.  `value` = proofs/s with the witness tables already resident in HBM; `e2e` = the same through
 the host-pointer C ABI call (pb200_prove), i.e. including the pinned-host -> device copy of every
-proof's witnesses and the device -> host read of the proof.  The roofline block describes the
-dominant kernel (MSM bucket accumulation), timed live with CUDA events on its launching stream.
+proof's witnesses and the device -> host read of the proof; `e2e_with_synthesis` additionally re-runs
+the circuit on the host for every proof (the composer's witness-only mode), which is what the
+reference's Prover::prove(rng, circuit) does first (src/compiler/prover.rs:425).  The roofline block
+describes the dominant kernel (MSM bucket accumulation), timed live with CUDA events on its launching
+stream.  `extra` carries the other BASELINE.json configs: one 2^20-gate proof (configs[2], N = 1) and the
+point-sharded MSM sweep 2^16..2^24 with its one NCCL all-gather (configs[3], every N).
 """
 import argparse
 import math
@@ -141,10 +145,26 @@ def run_ours(args):
     pool = ThreadPoolExecutor(inflight)
     pi_idx, pi_vals, n_pi = arrays.pi_idx, arrays.pi_vals, arrays.n_pi
 
+    def synthesize(slot):
+        """Prover::prove's first step (prover.rs:425): run the circuit again for its witness values; the table
+        lands straight in the slot's pinned staging buffer."""
+        h = ctypes.c_void_p()
+        check(L.pb200_composer_new(ctypes.byref(h)))
+        try:
+            check(L.pb200_composer_set_witness_only(h, 1))
+            check(L.pb200_composer_bench_circuit(h, 1 << LOG_GATES))
+            assert L.pb200_composer_witnesses(h) == n_wit
+            check(L.pb200_composer_export(h, None, None, host_wit[slot].data_ptr(), None, None))
+        finally:
+            L.pb200_composer_free(h)
+
     def one(slot, step, resident):
         bl = blinders_for(step * inflight + slot)
-        if resident:
-            check(L.pb200_prove_dev(prover._h, dev_wit[slot].data_ptr(), pi_idx, pi_vals, n_pi, bl, proofs[slot], None))
+        if resident == "synth":
+            synthesize(slot)
+            check(L.pb200_prove(prover._h, host_wit[slot].data_ptr(), n_wit, pi_idx, pi_vals, n_pi, bl, proofs[slot]))
+        elif resident:
+            check(L.pb200_prove_dev(prover._h, dev_wit[slot].data_ptr(), n_wit, pi_idx, pi_vals, n_pi, bl, proofs[slot], None))
         else:
             check(L.pb200_prove(prover._h, host_wit[slot].data_ptr(), n_wit, pi_idx, pi_vals, n_pi, bl, proofs[slot]))
 
@@ -187,6 +207,12 @@ def run_ours(args):
     ms_res = timed(args.steps, True)
     launches = L.pb200_launch_count() - launches0
     ms_e2e = timed(args.steps, False)
+    ms_synth = None
+    if args.circuit == "bench":
+        run_steps(1, "synth")
+        t_cpu0 = time.process_time()
+        ms_synth = timed(args.steps, "synth")
+        cpu_s_synth = time.process_time() - t_cpu0
     # Dominant kernel (MSM bucket accumulation), timed with CUDA events on its launching stream while
     # proofs run one at a time, so the event pairs bracket the kernel alone (with several proofs in
     # flight the kernels of different streams overlap and a per-kernel duration is not meaningful).
@@ -206,37 +232,59 @@ def run_ours(args):
     total_proofs = args.steps * inflight * world
     value = total_proofs / (ms_res * 1e-3)
     e2e_value = total_proofs / (ms_e2e * 1e-3)
+    # BASELINE.json configs[3]: every rank takes part in the point-sharded MSM sweep (one NCCL all-gather per MSM)
+    sweep = None if args.no_msm_sweep else msm_sweep(L, torch, rank, world, local, args)
     if rank != 0:
         finish_dist(world)
         return
-    # dominant kernel: MSM bucket accumulation
+    # dominant kernel: MSM bucket accumulation.  Both hot kernels are integer-multiply bound at 256/381-bit
+    # precision (~20 MAC per algorithmic byte against a machine balance of ~2.8), so the
+    # binding roofline is the ALU one; the HBM fraction is reported beside it.
     hbm_peak, peak_src = measured_peaks()
-    imad = ctypes.c_double()
+    imad, fp_peak = ctypes.c_double(), ctypes.c_double()
     check(L.pb200_imad_peak(ctypes.byref(imad)))
+    check(L.pb200_fp_product_peak(ctypes.byref(fp_peak)))
     acc_s = acc_ms.value * 1e-3
     adds_per_s = acc_adds.value / acc_s if acc_s else 0.0
     algo_bytes = 128.0 * acc_points.value  # 96 B affine base + 32 B scalar per MSM point
+    alu_peak = imad.value / IMAD_PER_ADD
+    alu_frac = adds_per_s / alu_peak if alu_peak else 0.0
+    hbm_achieved = algo_bytes / acc_s / 1e9 if acc_s else 0.0
+    traffic, traffic_src = measured_traffic()
     roof = {
-        "kernel": "k_msm_accumulate", "bound": "hbm",
-        "achieved": algo_bytes / acc_s / 1e9 if acc_s else 0.0, "peak": hbm_peak, "unit": "GB/s",
-        "frac": (algo_bytes / acc_s / 1e9 / hbm_peak) if acc_s else 0.0,
-        "traffic": TRAFFIC_PER_LAUNCH, "peak_source": peak_src,
+        "kernel": "k_msm_accumulate (+ k_msm_heavy_chunks / k_msm_heavy_combine for over-long buckets)", "bound": "alu",
+        "achieved": adds_per_s, "peak": alu_peak, "unit": "G1 adds/s", "frac": max(alu_frac, hbm_achieved / hbm_peak),
+        "peak_source": "pb200_imad_peak, measured in this run: register-only IMAD.WIDE.U32 issue rate / "
+                       f"{IMAD_PER_ADD} IMAD.WIDE per XYZZ mixed addition (SASS count)",
+        "imad_wide_per_s_measured": imad.value,
+        "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak, "peak_source": peak_src,
+                "algorithmic_bytes": "128 B per MSM point (96 B affine base + 32 B scalar, each once)"},
+        "traffic": traffic, "traffic_source": traffic_src,
         "launches": acc_launches.value, "avg_launch_ms": acc_ms.value / max(1, acc_launches.value),
+        "adds_per_launch": acc_adds.value / max(1, acc_launches.value),
         "share_of_step": (acc_ms.value / 3) / single_ms if single_ms else None,
-        "measured": "3 proofs issued one at a time after the timed region (exclusive kernel durations)",
+        "measured": "3 proofs issued one at a time after the timed region (exclusive kernel durations, CUDA events on the launching stream)",
         "single_stream_ms_per_proof": single_ms,
-        "alu": {"unit": "G1 adds/s", "achieved": adds_per_s, "peak": imad.value / IMAD_PER_ADD,
-                "frac": adds_per_s / (imad.value / IMAD_PER_ADD), "imad_wide_per_s_measured": imad.value,
-                "carry_chain_ceiling": {"fp_products_per_s": 30.3e9, "adds_per_s": 30.3e9 / FP_PRODUCTS_PER_ADD,
-                                        "frac": adds_per_s * FP_PRODUCTS_PER_ADD / 30.3e9,
-                                        "source": "tools/mulbench on this pool's B200: IMAD.WIDE.U32.X (carry in/out) issues at half the "
-                                                  "rate of carry-free IMAD.WIDE; 9.0 Fp-product equivalents per mixed addition"},
-                "note": "both hot kernels are IMAD-pipe bound at 256/381-bit precision; HBM fraction is reported because the contract asks for it"},
+        "carry_chain_ceiling": {"fp_products_per_s": fp_peak.value, "adds_per_s": fp_peak.value / FP_PRODUCTS_PER_ADD,
+                                "frac": adds_per_s * FP_PRODUCTS_PER_ADD / fp_peak.value if fp_peak.value else None,
+                                "source": "pb200_fp_product_peak, measured in this run: dependent chains of carry-chained Fp products "
+                                          "(IMAD.WIDE.U32.X issues at half the rate of the carry-free form); "
+                                          f"{FP_PRODUCTS_PER_ADD:.2f} Fp-product equivalents per mixed addition"},
     }
     ntt = ntt_microbench(L, torch, imad.value)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(arrays, 1)
+    extra = {}
+    if ms_synth is not None:
+        host_threads = len(os.sched_getaffinity(0))
+        extra["e2e_with_synthesis"] = {
+            "value": total_proofs / (ms_synth * 1e-3), "unit": "proofs/s",
+            "what": "every proof first re-runs the circuit on the host (native composer, witness-only mode: BenchCircuit<2^16>, "
+                    "as Prover::prove(rng, circuit) does, prover.rs:425), then pb200_prove with host witnesses",
+            "host_threads": inflight, "host_threads_available": host_threads,
+            "host_cpu_s_per_proof": cpu_s_synth / (args.steps * inflight),
+            "frac_of_value": (total_proofs / (ms_synth * 1e-3)) / value}
     line = {
         "metric": "proofs/sec @ 2^16 gates", "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -246,19 +294,133 @@ def run_ours(args):
                    "l2": "per-proof working set ~0.7 GB (prover key 240 MB + MSM tables 100 MB + scratch) > 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": inflight * (n_wit * 32 + n_pi * 32 + 14 * 32),
                 "d2h_bytes_per_step": inflight * (11 * 96 + 15 * 32)},
-        "gpu_launches": int(launches), "clocks": sampler.result(), "roofline": roof, "ntt": ntt,
+        "gpu_launches": int(launches), "clocks": sampler.result(), "roofline": roof, "ntt": ntt, "extra": extra,
     }
     if cpu:
         line["cpu_baseline"] = cpu
+    if sweep is not None:
+        extra["msm_sweep"] = sweep
+    if world == 1 and not args.no_proof20:
+        del prover, dev_wit  # make room: the 2^20-gate prover key is ~5 GB, its commit-key tables ~2.6 GB
+        torch.cuda.empty_cache()
+        extra.update(proof_2_20(L, torch))
     print(json.dumps(line), flush=True)
     finish_dist(world)
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_msm_accumulate launch (batch of 4 MSMs over 2^16+7
-# points: 364.9 MB + 22.9 MB) from the committed capture profiles/ncu_r01_accumulate.ncu-rep.  The
-# algorithmic 128 B/point would be 33.6 MB: the x11.5 is the deliberate table of window multiples
-# (16 x 96 B gathered per point), not a re-read to fix.
-TRAFFIC_PER_LAUNCH = 387.8e6
+def msm_sweep(L, torch, rank, world, local, args):
+    """BASELINE.json configs[3] / SURVEY.md section 8e-ii: one G1 MSM of 2^16 .. 2^24 points whose points are
+    partitioned across the ranks.  Every rank makes its slice of a seeded key [x^i]g on its own GPU, holds the
+    full scalar vector in HBM and reads its slice; plonk_b200.dist.ShardedCommitKey runs the slice MSM and the
+    device-resident ncclAllGather of the digit sums (pb200_msm_g1_allgather_dev) - or, below its size threshold,
+    the whole MSM on a replicated key with no collective.  The scalars repeat a random 4096-element block, so
+    the result is checked against [g p(x)]G from the closed form p(x) = B(x) * (x^n - 1) / (x^4096 - 1).
+    Timed with CUDA events on the launching stream, max over ranks, best of `iters`."""
+    import random
+
+    import torch.distributed as dist
+
+    from plonk_b200 import dist as pd
+    from plonk_b200._lib import check
+
+    comm = pd.NcclComm() if world > 1 else None
+    x, gs = SRS_X, SRS_G
+    threshold = 1 << 18
+    stream = torch.cuda.Stream()
+    rows = []
+    # replica of the first `threshold` points, for MSMs too small to be worth an exchange
+    rep_raw = ctypes.create_string_buffer(96 * threshold)
+    check(L.pb200_srs_setup_from_secret(mont(x), mont(gs), threshold, rep_raw))
+    for log_n in [int(v) for v in args.msm_sizes.split(",") if v]:
+        n = 1 << log_n
+        first, count = pd.shard_range(n, rank, world)
+        slice_raw = ctypes.create_string_buffer(96 * max(count, 1))
+        if count:  # [x^(first+i)] g = [x^i] ([x^first] g)
+            check(L.pb200_srs_setup_from_secret(mont(x), mont(gs * pow(x, first, R_MOD) % R_MOD), count, slice_raw))
+        key = pd.ShardedCommitKey(slice_raw.raw[: 96 * count], n, comm, threshold=threshold, replica_raw=rep_raw.raw[: 96 * min(n, threshold)])
+        del slice_raw
+        rng = random.Random(4096 + log_n)  # the same block on every rank
+        block = [rng.randrange(R_MOD) for _ in range(4096)]
+        blk = torch.frombuffer(bytearray(b"".join(mont(v) for v in block)), dtype=torch.int64).view(4096, 4)
+        sc = blk.repeat(n // 4096, 1).contiguous().cuda()
+        times = []
+        total = None
+        for it in range(args.msm_iters + 1):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            total = key.commit_dev(sc.data_ptr(), n, stream.cuda_stream)  # returns after its one synchronisation + host tail
+            e1.record(stream)
+            stream.synchronize()
+            ms = pd.max_over_ranks(e0.elapsed_time(e1), torch.device("cuda", local))
+            if it:
+                times.append(ms)
+        # [g * B(x) * (x^n - 1)/(x^4096 - 1)] G as a one-point "key"
+        bx = 0
+        for v in reversed(block):
+            bx = (bx * x + v) % R_MOD
+        geo = (pow(x, n, R_MOD) - 1) * pow(pow(x, 4096, R_MOD) - 1, -1, R_MOD) % R_MOD
+        want = ctypes.create_string_buffer(96)
+        check(L.pb200_srs_setup_from_secret(mont(1), mont(gs * bx * geo % R_MOD), 1, want))
+        ok = want.raw == total
+        best = min(times)
+        rows.append({"log_n": log_n, "gpus": world, "ms": best, "points_per_s": n / best * 1e3, "window_bits": key.window,
+                     "collective": "ncclAllGather of digit sums (device-resident)" if key.uses_collective(n) else "none (replicated key below the threshold)",
+                     "checked": bool(ok)})
+        key.free()
+        del sc
+        torch.cuda.empty_cache()
+        if not ok:
+            raise SystemExit(f"sharded MSM 2^{log_n} differs from [p(x)]g on rank {rank}")
+    if comm is not None:
+        comm.destroy()
+    return {"sizes": rows, "single_gpu_threshold_points": threshold,
+            "scalars": "random 4096-element block repeated (checkable in closed form; digit statistics of uniform scalars)"}
+
+
+def proof_2_20(L, torch):
+    """BASELINE.json configs[2]: one proof of the reference's BenchCircuit at 2^20 gates (quotient on the 4n coset
+    2^22, 2^20 + 7-point commit key) - byte parity at this size is tests/test_gpu_prover.py::test_gpu_prover_2_20_gates."""
+    from plonk_b200 import Prover
+    from plonk_b200._lib import check
+    from plonk_b200.gadgets import bench_circuit
+
+    log_gates = 20
+    t0 = time.time()
+    arrays = bench_circuit(1 << log_gates).arrays()
+    n_srs = (1 << log_gates) + 7
+    srs_raw = ctypes.create_string_buffer(n_srs * 96)
+    check(L.pb200_srs_setup_from_secret(mont(SRS_X), mont(SRS_G), n_srs, srs_raw))
+    prover = Prover(b"bench-2^20", arrays.constraints, arrays.selectors, arrays.wires, arrays.n_witnesses, srs_raw.raw)
+    setup_s = time.time() - t0
+    wit = torch.frombuffer(bytearray(arrays.witnesses), dtype=torch.uint8).cuda()
+    out = ctypes.create_string_buffer(1008)
+    stream = torch.cuda.Stream()
+    times = []
+    for it in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        check(L.pb200_prove_dev(prover._h, wit.data_ptr(), arrays.n_witnesses, arrays.pi_idx, arrays.pi_vals, arrays.n_pi, blinders_for(it), out, stream.cuda_stream))
+        e1.record(stream)
+        stream.synchronize()
+        if it:
+            times.append(e0.elapsed_time(e1))
+    return {"proof_2^20_ms": min(times), "proof_2^20": {"gates": arrays.constraints, "circuit": "reference BenchCircuit<2^20>", "ms_all": times,
+                                                        "compile_and_key_setup_s": setup_s, "proofs_in_flight": 1}}
+
+
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_msm_accumulate launch, from the text export of the
+    ncu --set full capture of THIS build's kernel (profiles/ncu_r02_accumulate.json, written by tools/ncu_export.py);
+    None when no capture of the current kernel is committed."""
+    p = os.path.join(ROOT, "profiles", "ncu_r02_accumulate.json")
+    try:
+        d = json.load(open(p))
+        return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"]), f"profiles/ncu_r02_accumulate.json ({d.get('kernel', '?')}, {d.get('launch', '?')})"
+    except (OSError, KeyError, ValueError):
+        return None, "no committed capture of this build's kernel"
 
 
 def ntt_microbench(L, torch, imad_peak):
@@ -318,7 +480,7 @@ def cpu_baseline(arrays, n_proofs):
     return {"value": n_proofs / dt, "unit": "proofs/s", "cores": threads, "kind": "port",
             "sample": f"{n_proofs} proof(s) of the same 2^16-gate circuit, C++/OpenMP restatement of the reference prover "
                       f"(the Rust crate cannot be built here: no cargo/rustc); "
-                      f"thread count = fastest of T, T/2, T/4 for the {cref.threads()} usable host threads",
+                      f"{cref.thread_policy()}",
             "coset_ntt_2^19": {"ms": ntt_s * 1e3, "butterflies_per_s": (n19 // 2) * (LOG_GATES + 3) / ntt_s},
             "msm_2^16": {"ms": msm_s * 1e3, "points_per_s": SRS_POINTS / msm_s,
                          "bucket_adds_per_s": SRS_POINTS * math.ceil(255 / window) / msm_s, "window_bits": window}}
@@ -354,8 +516,8 @@ def run_reference(args):
         prover.prove(blinders_for(1000 + i), arrays)
     dt = time.time() - t0
     value = args.steps / dt
-    sample = (f"each step = 1 proof of the 2^16-gate workload on {threads} host threads (fastest of T, T/2, T/4 for the "
-              f"{cref.threads()} usable ones; C++/OpenMP restatement; the Rust reference cannot be built here)")
+    sample = (f"each step = 1 proof of the 2^16-gate workload; {cref.thread_policy()}; C++/OpenMP restatement "
+              "(the Rust reference cannot be built here)")
     print(json.dumps({
         "impl": "reference", "metric": "proofs/sec @ 2^16 gates", "value": value, "unit": "proofs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
@@ -374,6 +536,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--inflight", type=int, default=int(os.environ.get("PB200_INFLIGHT", "8")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-msm-sweep", action="store_true", help="skip extra.msm_sweep (BASELINE.json configs[3])")
+    ap.add_argument("--msm-sizes", default="16,18,20,22,24", help="log2 point counts of the sharded-MSM sweep")
+    ap.add_argument("--msm-iters", type=int, default=3)
+    ap.add_argument("--no-proof20", action="store_true", help="skip extra.proof_2^20_ms (BASELINE.json configs[2], N = 1 only)")
     ap.add_argument("--circuit", default="bench", choices=["bench", "synthetic"],
                     help="bench = the reference's BenchCircuit<2^16> (default); synthetic = random arithmetic gates")
     args = ap.parse_args()

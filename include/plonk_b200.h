@@ -55,7 +55,11 @@ typedef struct pb200_srs pb200_srs_t;
 typedef struct pb200_prover pb200_prover_t;
 
 /* ---- process / device ------------------------------------------------------------------- */
-int pb200_init(int device);                 /* idempotent; selects the device for this process */
+/* Selects the device for this process.  Idempotent for the same device; ONE device per process: the
+ * twiddle / coset tables, per-thread streams and pinned staging buffers are created on the first device
+ * used, so a second call naming another device returns PB200_ERR_INVALID_ARG (multi-GPU hosts run one
+ * process per GPU, as bench.py does under torchrun). */
+int pb200_init(int device);
 const char* pb200_last_error(void);         /* thread-local description of the last failure */
 int pb200_device_sync(void);
 /* Number of kernels launched by this library since process start (for bench.py's gpu_launches). */
@@ -76,6 +80,12 @@ int pb200_ntt_dev(const uint64_t* d_in, size_t in_len, uint64_t* d_out, uint32_t
 /* ---- KZG commit key + MSM ---------------------------------------------------------------- */
 /* raw_points: n_points x 96 bytes (layout above) = CommitKey::powers_of_g. */
 int pb200_srs_upload(const uint8_t* raw_points, size_t n_points, pb200_srs_t** out);
+/* Same with an explicit bucket-window width (bits); 0 = automatic (what pb200_srs_upload picks from
+ * n_points).  The ranks of a point-sharded MSM (pb200_msm_g1_allgather*) must use ONE width for all slices:
+ * take pb200_msm_window_for(largest slice) on every rank. */
+int pb200_srs_upload_window(const uint8_t* raw_points, size_t n_points, int window_bits, pb200_srs_t** out);
+int pb200_msm_window_for(size_t n_points);    /* the automatic choice for a key of n_points */
+int pb200_srs_window(const pb200_srs_t* srs); /* the width a key was uploaded with */
 void pb200_srs_free(pb200_srs_t* srs);
 size_t pb200_srs_len(const pb200_srs_t* srs);
 
@@ -97,9 +107,29 @@ int pb200_msm_g1_range(const pb200_srs_t* srs, size_t first, const uint64_t* sca
  * stride `stride`).  The per-rank partial results - one affine point per batch entry - are exchanged
  * with a single ncclAllGather on `nccl_comm` (an ncclComm_t of `n_ranks` ranks created by the caller;
  * NCCL is looked up in the process at run time) and added locally in rank order, so every rank
- * receives the same batch x 96-byte result.  This is the only collective on the path. */
+ * receives the same batch x 96-byte result.  This is the only collective on the path.  (Since round 2 the
+ * exchange is the device-resident one described under pb200_msm_g1_allgather_dev; this entry point only adds
+ * the host -> device copy of the scalars.) */
 int pb200_msm_g1_allgather(const pb200_srs_t* srs_slice, const uint64_t* scalars_slice, size_t n_scalars,
                            uint32_t batch, size_t stride, void* nccl_comm, int n_ranks, uint64_t* out_affine);
+/* Same with the scalar slice already resident in HBM.  The exchange is device to device on `stream`
+ * (NULL = the calling thread's pb200 stream), straight behind the reduction kernels: what travels is each
+ * rank's per-digit bucket sums ((ndig + 1) x 192 bytes per batch entry plus a 16-byte header), the per-digit
+ * sums are added across ranks and ONE Horner + affine normalisation finishes the result on every rank; the
+ * call synchronises the stream once.  A rank whose local part fails still joins the collective (flagged in
+ * its header), so its peers return PB200_ERR_CUDA instead of hanging; slices uploaded with different window
+ * widths are reported as PB200_ERR_INVALID_ARG on every rank.  An empty slice (n_scalars = 0) is allowed. */
+int pb200_msm_g1_allgather_dev(const pb200_srs_t* srs_slice, const uint64_t* d_scalars_slice, size_t n_scalars,
+                               uint32_t batch, size_t stride, void* nccl_comm, int n_ranks,
+                               uint64_t* out_affine_host, void* stream);
+
+/* The host tail of that exchange on its own (no GPU needed): `parts` holds n_parts x batch records of
+ * *words_per_entry 32-bit words - the (ndig + 1) XYZZ digit sums D_0 .. D_{ndig-1}, sum A_G a partial MSM with
+ * window width `window_bits` leaves (part-major) - and out_affine receives batch x 96 bytes:
+ *   R = sum_parts [ A + g * sum_j 2^shift_j D_j ],  added digit by digit, then one Horner and one shared inversion.
+ * With parts = NULL only *words_per_entry is written. */
+int pb200_msm_combine_parts(const uint32_t* parts, int n_parts, int window_bits, uint32_t batch,
+                            uint64_t* out_affine, size_t* words_per_entry);
 
 /* PublicParameters::setup with explicit secrets (srs.rs:61-100): out[i] = [g_scalar * x^i] G1, as
  * n_points x 96-byte raw points.  Test/bench helper - a real SRS comes from a ceremony. */
@@ -142,15 +172,20 @@ int pb200_prover_commitments(const pb200_prover_t* prover, uint8_t* out_15x48);
 int pb200_prove(const pb200_prover_t* prover, const uint64_t* witnesses, size_t n_witnesses,
                 const uint64_t* pi_idx, const uint64_t* pi_vals, size_t n_pi,
                 const uint64_t* blinders, uint8_t* out_proof);
-/* Same with the witness table already resident in HBM (pi_* and blinders stay host pointers). */
-int pb200_prove_dev(const pb200_prover_t* prover, const uint64_t* d_witnesses,
+/* Same with the witness table already resident in HBM (pi_* and blinders stay host pointers);
+ * n_witnesses is the length of the device table and must equal the compiled circuit's.
+ * Both calls return PB200_ERR_INVALID_ARG when n_pi > 0 and pi_idx / pi_vals is NULL, when a position is
+ * outside the circuit, or when pi_idx is not strictly increasing (the reference's BTreeMap cannot hold
+ * duplicates).  Largest circuit: 2^28 gates (the quotient domain 8n must stay below 2^32, domain.rs:132-137). */
+int pb200_prove_dev(const pb200_prover_t* prover, const uint64_t* d_witnesses, size_t n_witnesses,
                     const uint64_t* pi_idx, const uint64_t* pi_vals, size_t n_pi,
                     const uint64_t* blinders, uint8_t* out_proof, void* stream);
 
 /* ---- measurement helpers ----------------------------------------------------------------- */
-/* In-library CUDA-event timing of the MSM bucket-accumulation kernel (the dominant kernel of a
- * proof) on its launching stream: enable resets the counters; read returns the summed kernel time,
- * the G1 mixed additions it executed, its launch count and the MSM points processed. */
+/* In-library CUDA-event timing of the MSM bucket-accumulation phase (k_msm_accumulate, the dominant
+ * kernel of a proof, plus the two heavy-bucket kernels behind it) on its launching stream: enable resets
+ * the counters; read returns the summed time, the G1 mixed additions executed (one per non-zero window
+ * digit), the launch count and the MSM points processed. */
 int pb200_profile_enable(int on);
 int pb200_profile_read(double* accumulate_ms, uint64_t* accumulate_adds, uint64_t* accumulate_launches,
                        uint64_t* msm_points);
@@ -163,6 +198,10 @@ int pb200_profile_read(double* accumulate_ms, uint64_t* accumulate_adds, uint64_
 int pb200_g1_lagrange_key(const uint64_t* points, size_t n, uint64_t* out);
 /* Register-only IMAD.WIDE microbenchmark: returns achieved 32x32+64 multiply-adds per second. */
 int pb200_imad_peak(double* mads_per_sec);
+/* Dependent chains of carry-chained Fp (381-bit) Montgomery products, 1024 threads per SM: achieved products
+ * per second - the ceiling the G1 kernels are measured against (IMAD.WIDE.U32.X, the carry-in/out form every
+ * multi-limb product needs, issues at half the rate of the carry-free IMAD.WIDE that pb200_imad_peak times). */
+int pb200_fp_product_peak(double* products_per_sec);
 /* Elementwise Fr / Fp Montgomery products on the device (kernel self-test of the arithmetic). */
 int pb200_selftest_fr_mul(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
 int pb200_selftest_fp_mul(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);

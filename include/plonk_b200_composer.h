@@ -64,6 +64,11 @@ enum pb200_point_op { PB200_POINT_ADD = 0, PB200_POINT_SUB = 1, PB200_POINT_NEG 
 typedef struct pb200_composer pb200_composer_t;
 
 int pb200_composer_new(pb200_composer_t** out);
+/* Witness-only mode, for the composer that Prover::prove runs per proof (src/compiler/prover.rs:425): the
+ * circuit is re-run for its witness table and public inputs only - the gate layout is the one the prover
+ * was compiled from - so gates are validated and counted but not stored; pb200_composer_export then
+ * refuses `selectors` / `wires`.  Switch it on right after pb200_composer_new. */
+int pb200_composer_set_witness_only(pb200_composer_t* c, int on);
 void pb200_composer_free(pb200_composer_t* c);
 size_t pb200_composer_constraints(const pb200_composer_t* c);
 size_t pb200_composer_witnesses(const pb200_composer_t* c);

@@ -72,41 +72,41 @@ def _cgroup_cpu_limit() -> Optional[int]:
 _best_threads: Optional[int] = None
 
 
-def best_threads() -> int:
-    """Thread count at which the restated prover is fastest on this host: every core this process
-    may run on, capped by the container's CPU quota, and - because SMT siblings or a shared host can
-    make "all of them" slower than half - checked against T/2 and T/4 on a short NTT + MSM sample.
-    The CPU baseline should be the reference at its best, not at its most oversubscribed."""
-    global _best_threads
-    if _best_threads is not None:
-        return _best_threads
-    if os.environ.get("PB200_CPU_THREADS"):
-        _best_threads = threads()
-        return _best_threads
-    import time
+def _physical_cores() -> int:
+    """Distinct physical cores among the CPUs this process may run on (SMT siblings counted once)."""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+    cores = set()
+    for c in cpus:
+        try:
+            sib = open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list").read().strip()
+        except OSError:
+            sib = str(c)
+        cores.add(sib)
+    return max(1, len(cores))
 
-    top = threads()
-    limit = _cgroup_cpu_limit()
-    if limit:
-        top = min(top, limit)
-    cands = sorted({max(1, top), max(1, top // 2), max(1, top // 4)}, reverse=True)
-    if len(cands) == 1:
-        _best_threads = cands[0]
-        return _best_threads
-    n = 1 << 14
-    srs = srs_from_secret(n, 0x1234567, 0x7654321, cands[-1])
-    vec = b"".join(R.fr_to_mont_bytes((i * 0x9E3779B97F4A7C15 + 12345) % R.R_MOD) for i in range(1 << 10)) * ((1 << 17) >> 10)
-    best, best_t = cands[0], None
-    for t in cands:
-        ntt(vec, 17, 0, 1, t)  # warm the thread pool at this width
-        t0 = time.time()
-        ntt(vec, 17, 0, 1, t)
-        msm(srs, vec[: n * 32], t)
-        dt = time.time() - t0
-        if best_t is None or dt < best_t * 0.95:  # prefer more threads unless fewer is clearly faster
-            best, best_t = t, dt if best_t is None else min(dt, best_t)
-    _best_threads = best
-    return best
+
+def best_threads() -> int:
+    """Thread count of the CPU baseline - ONE fixed policy, so that the number does not swing with a
+    calibration run: every physical core this process may run on (SMT siblings once), capped by the
+    container's CPU quota; PB200_CPU_THREADS overrides.  (Round 1 picked the fastest of T, T/2, T/4 on a
+    short sample, which chose 16, 48 or 96 threads on different boxes.)"""
+    global _best_threads
+    if _best_threads is None:
+        if os.environ.get("PB200_CPU_THREADS"):
+            _best_threads = threads()
+        else:
+            top = _physical_cores()
+            limit = _cgroup_cpu_limit()
+            _best_threads = max(1, min(top, limit) if limit else top)
+    return _best_threads
+
+
+def thread_policy() -> str:
+    return (f"{best_threads()} threads = every physical core usable by this process ({threads()} logical CPUs), capped by the "
+            "cgroup CPU quota; fixed policy, PB200_CPU_THREADS overrides")
 
 
 def _default_threads(work_items: int) -> int:

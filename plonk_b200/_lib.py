@@ -20,22 +20,22 @@ PB200_ERR_POINT_MALFORMED = -10
 
 _lib = None
 
-# every symbol include/plonk_b200.h declares (tests/test_abi.py checks the list against the header)
+# every symbol include/plonk_b200.h declares (tests/test_host_logic.py checks the list against the header)
 EXPORTS = [
     "pb200_init", "pb200_last_error", "pb200_device_sync", "pb200_launch_count",
     "pb200_ntt", "pb200_ntt_dev",
-    "pb200_srs_upload", "pb200_srs_free", "pb200_srs_len",
-    "pb200_msm_g1", "pb200_msm_g1_dev", "pb200_msm_g1_range", "pb200_msm_g1_allgather",
+    "pb200_srs_upload", "pb200_srs_upload_window", "pb200_msm_window_for", "pb200_srs_window", "pb200_srs_free", "pb200_srs_len",
+    "pb200_msm_g1", "pb200_msm_g1_dev", "pb200_msm_g1_range", "pb200_msm_g1_allgather", "pb200_msm_g1_allgather_dev", "pb200_msm_combine_parts",
     "pb200_g1_compress", "pb200_g1_decompress", "pb200_g1_add_affine", "pb200_srs_setup_from_secret", "pb200_g1_lagrange_key",
     "pb200_profile_enable", "pb200_profile_read",
     "pb200_prover_new", "pb200_prover_free", "pb200_prover_commitments", "pb200_prove", "pb200_prove_dev",
-    "pb200_imad_peak", "pb200_selftest_fr_mul", "pb200_selftest_fp_mul", "pb200_selftest_fp_ops",
+    "pb200_imad_peak", "pb200_fp_product_peak", "pb200_selftest_fr_mul", "pb200_selftest_fp_mul", "pb200_selftest_fp_ops",
 ]
 
 
 # every symbol include/plonk_b200_composer.h declares (host-side circuit front end)
 COMPOSER_EXPORTS = [
-    "pb200_composer_new", "pb200_composer_free", "pb200_composer_constraints", "pb200_composer_witnesses",
+    "pb200_composer_new", "pb200_composer_set_witness_only", "pb200_composer_free", "pb200_composer_constraints", "pb200_composer_witnesses",
     "pb200_composer_public_inputs", "pb200_composer_witness_value", "pb200_composer_append_witness",
     "pb200_composer_append_gate", "pb200_composer_append_evaluated_output", "pb200_composer_gate_add",
     "pb200_composer_append_constant", "pb200_composer_append_public", "pb200_composer_assert_equal",
@@ -80,6 +80,14 @@ def lib() -> ctypes.CDLL:
         L.pb200_msm_g1_dev.argtypes = L.pb200_msm_g1.argtypes + [c.c_void_p]
         L.pb200_msm_g1_range.argtypes = [c.c_void_p, c.c_size_t, c.c_void_p, c.c_size_t, c.c_void_p]
         L.pb200_msm_g1_allgather.argtypes = [c.c_void_p, c.c_void_p, c.c_size_t, c.c_uint32, c.c_size_t, c.c_void_p, c.c_int, c.c_void_p]
+        L.pb200_msm_g1_allgather_dev.argtypes = L.pb200_msm_g1_allgather.argtypes + [c.c_void_p]
+        L.pb200_msm_combine_parts.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_uint32, c.c_void_p, c.POINTER(c.c_size_t)]
+        L.pb200_srs_upload_window.argtypes = [c.c_void_p, c.c_size_t, c.c_int, c.POINTER(c.c_void_p)]
+        L.pb200_msm_window_for.argtypes = [c.c_size_t]
+        L.pb200_srs_window.argtypes = [c.c_void_p]
+        L.pb200_g1_lagrange_key.argtypes = [c.c_void_p, c.c_size_t, c.c_void_p]
+        L.pb200_selftest_fp_ops.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_size_t]
+        L.pb200_device_sync.argtypes = []
         L.pb200_g1_compress.argtypes = [c.c_void_p, c.c_void_p]
         L.pb200_g1_decompress.argtypes = [c.c_void_p, c.c_size_t, c.c_int, c.c_void_p]
         L.pb200_g1_add_affine.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p]
@@ -88,11 +96,12 @@ def lib() -> ctypes.CDLL:
         L.pb200_prover_free.restype = None
         L.pb200_prover_commitments.argtypes = [c.c_void_p, c.c_void_p]
         L.pb200_prove.argtypes = [c.c_void_p, c.c_void_p, c.c_size_t, c.c_void_p, c.c_void_p, c.c_size_t, c.c_void_p, c.c_void_p]
-        L.pb200_prove_dev.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_size_t, c.c_void_p, c.c_void_p, c.c_void_p]
+        L.pb200_prove_dev.argtypes = [c.c_void_p, c.c_void_p, c.c_size_t, c.c_void_p, c.c_void_p, c.c_size_t, c.c_void_p, c.c_void_p, c.c_void_p]
         L.pb200_srs_setup_from_secret.argtypes = [c.c_void_p, c.c_void_p, c.c_size_t, c.c_void_p]
         L.pb200_profile_enable.argtypes = [c.c_int]
         L.pb200_profile_read.argtypes = [c.POINTER(c.c_double), c.POINTER(c.c_uint64), c.POINTER(c.c_uint64), c.POINTER(c.c_uint64)]
         L.pb200_imad_peak.argtypes = [c.POINTER(c.c_double)]
+        L.pb200_fp_product_peak.argtypes = [c.POINTER(c.c_double)]
         L.pb200_selftest_fr_mul.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_size_t]
         L.pb200_selftest_fp_mul.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_size_t]
         _bind_composer(L)
@@ -105,6 +114,7 @@ def _bind_composer(L) -> None:
     H, W, P, I = c.c_void_p, c.c_uint32, c.c_void_p, c.c_int
     sig = {
         "pb200_composer_new": [c.POINTER(c.c_void_p)],
+        "pb200_composer_set_witness_only": [H, I],
         "pb200_composer_witness_value": [H, W, P],
         "pb200_composer_append_witness": [H, P, P],
         "pb200_composer_append_gate": [H, P, P, P, I],

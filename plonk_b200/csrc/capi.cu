@@ -88,12 +88,19 @@ int ntt_run(const uint64_t* d_in, size_t in_len, uint64_t* d_out, uint32_t log_n
             uint32_t batch, size_t in_stride, size_t out_stride, cudaStream_t st, Arena* ar);
 int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_t n, uint32_t batch,
             size_t stride, uint64_t* out_affine_host, cudaStream_t st, Arena* ar);
-int srs_upload(const uint8_t* raw, size_t n_points, pb200_srs** out);
+int srs_upload(const uint8_t* raw, size_t n_points, pb200_srs** out, int window_bits);
+typedef int (*nccl_all_gather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
+int msm_allgather(const pb200_srs* srs, const uint64_t* scalars, bool scalars_on_device, size_t n, uint32_t batch, size_t stride,
+                  nccl_all_gather_fn all_gather, void* comm, int n_ranks, int* nccl_rc, uint64_t* out_affine_host, cudaStream_t st);
+int msm_combine_parts(const uint32_t* parts, int n_parts, int window_bits, uint32_t batch, uint64_t* out_affine_host, size_t* words_per_entry);
 int selftest_mul(int which, const uint64_t* a, const uint64_t* b, uint64_t* o, size_t n);
 int imad_peak(double* out);
+int fp_product_peak(double* out);
 int lagrange_key_dev(const uint4* d_in, int log_n, uint4* d_out, cudaStream_t st);
 int selftest_fp_ops(const uint64_t* a, const uint64_t* b, const uint64_t* c, const uint64_t* d, uint64_t* o, size_t n);
 size_t srs_len(const pb200_srs* s);
+int srs_window(const pb200_srs* s);
+int msm_window_for(size_t n_points);
 int srs_setup(const uint64_t* x_mont, const uint64_t* g_scalar_mont, size_t n, uint8_t* out_raw);
 int g1_decompress(const uint8_t* in, size_t n, int check_subgroup, uint8_t* out_raw);
 extern std::atomic<int> g_prof_on;
@@ -111,6 +118,10 @@ int pb200_init(int device) {
     int count = 0;
     PB_CUDA(cudaGetDeviceCount(&count));
     if (device < 0 || device >= count) return fail(PB200_ERR_CUDA, "no such CUDA device");
+    // One device per process: twiddle/coset tables, per-thread streams and pinned buffers are created on
+    // the first device used and are not keyed by device.
+    if (g_device >= 0 && g_device != device)
+      return fail(PB200_ERR_INVALID_ARG, "pb200_init: this process is already bound to another CUDA device (one device per process)");
     PB_CUDA(cudaSetDevice(device));
     g_device = device;
   }
@@ -166,8 +177,16 @@ int pb200_ntt(const uint64_t* in, size_t in_len, uint64_t* out, uint32_t log_n, 
 int pb200_srs_upload(const uint8_t* raw_points, size_t n_points, pb200_srs_t** out) {
   PB_TRY(ensure_init());
   if (!raw_points || !out) return fail(PB200_ERR_INVALID_ARG, "null argument");
-  return srs_upload(raw_points, n_points, out);
+  return srs_upload(raw_points, n_points, out, 0);
 }
+int pb200_srs_upload_window(const uint8_t* raw_points, size_t n_points, int window_bits, pb200_srs_t** out) {
+  PB_TRY(ensure_init());
+  if (!raw_points || !out) return fail(PB200_ERR_INVALID_ARG, "null argument");
+  if (window_bits != 0 && (window_bits < 2 || window_bits > 20)) return fail(PB200_ERR_INVALID_ARG, "window_bits must be 0 (automatic) or in 2..=20");
+  return srs_upload(raw_points, n_points, out, window_bits);
+}
+int pb200_srs_window(const pb200_srs_t* srs) { return srs ? srs_window(srs) : 0; }
+int pb200_msm_window_for(size_t n_points) { return msm_window_for(n_points); }
 void pb200_srs_free(pb200_srs_t* srs) {
   if (srs) srs_free(srs);
 }
@@ -230,41 +249,35 @@ const NcclApi* nccl_api() {
 }
 }  // namespace
 
+static int allgather_common(const pb200_srs_t* srs_slice, const uint64_t* scalars, bool on_device, size_t n_scalars, uint32_t batch,
+                            size_t stride, void* nccl_comm, int n_ranks, uint64_t* out_affine, cudaStream_t st) {
+  if (!srs_slice || !out_affine || !nccl_comm || n_ranks < 1 || !batch || (!scalars && n_scalars)) return fail(PB200_ERR_INVALID_ARG, "null or empty argument");
+  if (n_scalars > srs_len(srs_slice)) return fail(PB200_ERR_DEGREE_TOO_LARGE, "more scalars than commit-key points");
+  const NcclApi* nccl = nccl_api();
+  if (!nccl) return fail(PB200_ERR_NOT_READY, "libnccl.so.2 (ncclAllGather) is not available in this process");
+  int nrc = 0;
+  const int rc = msm_allgather(srs_slice, scalars, on_device, n_scalars, batch, stride, nccl->all_gather, nccl_comm, n_ranks, &nrc, out_affine, st);
+  if (nrc != 0) return fail(PB200_ERR_CUDA, "ncclAllGather", nccl->error_string ? nccl->error_string(nrc) : "");
+  return rc;
+}
+
 int pb200_msm_g1_allgather(const pb200_srs_t* srs_slice, const uint64_t* scalars_slice, size_t n_scalars, uint32_t batch,
                            size_t stride, void* nccl_comm, int n_ranks, uint64_t* out_affine) {
   PB_TRY(ensure_init());
-  if (!srs_slice || !out_affine || !nccl_comm || n_ranks < 1 || !batch) return fail(PB200_ERR_INVALID_ARG, "null or empty argument");
-  const NcclApi* nccl = nccl_api();
-  if (!nccl) return fail(PB200_ERR_NOT_READY, "libnccl.so.2 (ncclAllGather) is not available in this process");
-  // 1. this rank's partial sums over its slice of the key
-  std::vector<uint64_t> mine((size_t)batch * 12);
-  PB_TRY(msm_host(srs_slice, 0, scalars_slice, n_scalars, batch, stride, mine.data()));
-  // 2. the one exchange step: 96 bytes per batch entry and rank (a G1 addition is not an NCCL reduction)
-  cudaStream_t st = thread_stream();
-  const size_t part = (size_t)batch * 96;
-  ScratchScope scope(nullptr, st);
-  uint8_t *d_send = nullptr, *d_recv = nullptr;
-  PB_ALLOC(scope, d_send, part);
-  PB_ALLOC(scope, d_recv, part * n_ranks);
-  std::vector<uint64_t> all((size_t)n_ranks * batch * 12);
-  cudaError_t e = cudaMemcpyAsync(d_send, mine.data(), part, cudaMemcpyHostToDevice, st);
-  int nrc = 0;
-  if (e == cudaSuccess) nrc = nccl->all_gather(d_send, d_recv, part, /*ncclUint8*/ 1, nccl_comm, st);
-  if (e == cudaSuccess && nrc == 0) e = cudaMemcpyAsync(all.data(), d_recv, part * n_ranks, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess && nrc == 0) e = stream_wait(st);
-  if (nrc != 0) return fail(PB200_ERR_CUDA, "ncclAllGather", nccl->error_string ? nccl->error_string(nrc) : "");
-  PB_CUDA(e);
-  // 3. every rank adds the partials in rank order
-  for (uint32_t b = 0; b < batch; b++) {
-    uint64_t acc[12] = {0};
-    for (int r = 0; r < n_ranks; r++) {
-      uint64_t sum[12];
-      PB_TRY(pb200_g1_add_affine(acc, all.data() + ((size_t)r * batch + b) * 12, sum));
-      memcpy(acc, sum, sizeof acc);
-    }
-    memcpy(out_affine + (size_t)b * 12, acc, sizeof acc);
-  }
-  return 0;
+  return allgather_common(srs_slice, scalars_slice, false, n_scalars, batch, stride, nccl_comm, n_ranks, out_affine, thread_stream());
+}
+
+int pb200_msm_g1_allgather_dev(const pb200_srs_t* srs_slice, const uint64_t* d_scalars_slice, size_t n_scalars, uint32_t batch,
+                               size_t stride, void* nccl_comm, int n_ranks, uint64_t* out_affine_host, void* stream) {
+  PB_TRY(ensure_init());
+  return allgather_common(srs_slice, d_scalars_slice, true, n_scalars, batch, stride, nccl_comm, n_ranks, out_affine_host,
+                          stream ? (cudaStream_t)stream : thread_stream());
+}
+
+int pb200_msm_combine_parts(const uint32_t* parts, int n_parts, int window_bits, uint32_t batch, uint64_t* out_affine,
+                            size_t* words_per_entry) {
+  if (window_bits < 2 || window_bits > 20 || n_parts < 0 || (parts && !out_affine)) return fail(PB200_ERR_INVALID_ARG, "bad argument");
+  return msm_combine_parts(parts, n_parts, window_bits, batch, out_affine, words_per_entry);
 }
 
 int pb200_g1_compress(const uint64_t* affine_raw, uint8_t out48[48]) {
@@ -341,6 +354,11 @@ int pb200_g1_lagrange_key(const uint64_t* points, size_t n, uint64_t* out) {
 int pb200_imad_peak(double* mads_per_sec) {
   PB_TRY(ensure_init());
   return imad_peak(mads_per_sec);
+}
+int pb200_fp_product_peak(double* products_per_sec) {
+  PB_TRY(ensure_init());
+  if (!products_per_sec) return fail(PB200_ERR_INVALID_ARG, "null argument");
+  return fp_product_peak(products_per_sec);
 }
 int pb200_selftest_fr_mul(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
   PB_TRY(ensure_init());

@@ -14,7 +14,23 @@ namespace pbc {
 // ---------------------------------------------------------------------------------------------
 // Fr helpers
 // ---------------------------------------------------------------------------------------------
-Fr fr_u64(uint64_t x) { return Fr::from_u64(x); }
+Fr fr_u64(uint64_t x) {
+  static const std::array<Fr, 16> small = [] {  // the gadgets mostly ask for bits, quads and tiny constants
+    std::array<Fr, 16> t;
+    for (uint64_t i = 0; i < 16; i++) t[i] = Fr::from_u64(i);
+    return t;
+  }();
+  return x < 16 ? small[x] : Fr::from_u64(x);
+}
+
+// q * v for a selector coefficient, which is nearly always 0, 1 or -1
+static inline void add_term(Fr& acc, const Fr& q, const Fr& v) {
+  if (q.is_zero()) return;
+  if (q == Fr::one())
+    acc = acc + v;
+  else
+    acc = acc + q * v;
+}
 
 static Fr fr_from_canonical(const uint64_t limbs[4]) {
   Fr r;
@@ -77,13 +93,72 @@ JubJubAffine jj_add(const JubJubAffine& p, const JubJubAffine& q) {
 
 JubJubAffine jj_neg(const JubJubAffine& p) { return {p.u.neg(), p.v}; }
 
-JubJubAffine jj_mul(const JubJubAffine& p, const uint64_t k[4]) {
-  JubJubAffine acc = jj_identity();
+// ---- extended coordinates (X : Y : Z : T), u = X/Z, v = Y/Z, T = XY/Z ---------------------------
+// The gadgets below need long chains of curve additions whose every intermediate value becomes a
+// witness.  The affine law costs one field inversion (~380 products) per addition; the chains are
+// therefore run in extended coordinates (add-2008-hwcd-3 for a = -1, unified: it also doubles) and all
+// their points normalised together with ONE inversion (Montgomery's trick).  Affine coordinates are
+// unique, so the witness values are exactly those of the affine law; its one special case - a vanishing
+// denominator, which jj_add maps to the identity like the reference's `sum.get_z() == 0` branch
+// (point.rs:226-231) - is Z3 = (D - C)(D + C) = 0 here and gets the same treatment.
+struct JubJubExt {
+  Fr x, y, z, t;
+};
+static JubJubExt ext_identity() { return {Fr::zero(), Fr::one(), Fr::one(), Fr::zero()}; }
+static JubJubExt ext_from_affine(const JubJubAffine& p) {
+  if (p.u.is_zero()) return {p.u, p.v, Fr::one(), Fr::zero()};
+  return {p.u, p.v, Fr::one(), p.u * p.v};
+}
+static const Fr& edwards_2d() {
+  static const Fr d2 = edwards_d().dbl();
+  return d2;
+}
+static JubJubExt ext_add(const JubJubExt& p, const JubJubExt& q) {
+  const Fr a = (p.y - p.x) * (q.y - q.x), b = (p.y + p.x) * (q.y + q.x);
+  const Fr c = p.t * edwards_2d() * q.t, d = (p.z * q.z).dbl();
+  const Fr e = b - a, f = d - c, g = d + c, h = b + a;
+  JubJubExt r = {e * f, g * h, f * g, e * h};
+  if (r.z.is_zero()) return ext_identity();
+  return r;
+}
+static bool ext_is_identity(const JubJubExt& p) { return p.x.is_zero() && p.y == p.z; }
+// all points to affine with one inversion (none of the Z is zero: ext_add never returns such a point)
+static void ext_batch_to_affine(const std::vector<JubJubExt>& in, std::vector<JubJubAffine>& out) {
+  const size_t n = in.size();
+  out.resize(n);
+  if (!n) return;
+  std::vector<Fr> pre(n);
+  Fr acc = Fr::one();
+  for (size_t i = 0; i < n; i++) {
+    pre[i] = acc;
+    acc = acc * in[i].z;
+  }
+  Fr inv = acc.inv();
+  for (size_t i = n; i-- > 0;) {
+    const Fr zi = inv * pre[i];
+    inv = inv * in[i].z;
+    out[i] = {in[i].x * zi, in[i].y * zi};
+  }
+}
+static JubJubExt ext_mul(const JubJubAffine& p, const uint64_t k[4]) {
+  const JubJubExt pe = ext_from_affine(p);
+  JubJubExt acc = ext_identity();
+  bool started = false;
   for (int i = 255; i >= 0; i--) {
-    acc = jj_add(acc, acc);
-    if ((k[i >> 6] >> (i & 63)) & 1) acc = jj_add(acc, p);
+    if (started) acc = ext_add(acc, acc);
+    if ((k[i >> 6] >> (i & 63)) & 1) {
+      acc = started ? ext_add(acc, pe) : pe;
+      started = true;
+    }
   }
   return acc;
+}
+
+JubJubAffine jj_mul(const JubJubAffine& p, const uint64_t k[4]) {
+  std::vector<JubJubExt> one(1, ext_mul(p, k));
+  std::vector<JubJubAffine> out;
+  ext_batch_to_affine(one, out);
+  return out[0];
 }
 
 bool jj_is_on_curve(const JubJubAffine& p) {
@@ -91,7 +166,19 @@ bool jj_is_on_curve(const JubJubAffine& p) {
   return v2 - u2 == Fr::one() + edwards_d() * u2 * v2;
 }
 
-bool jj_is_torsion_free(const JubJubAffine& p) { return jj_mul(p, kJubJubOrder) == jj_identity(); }
+bool jj_is_torsion_free(const JubJubAffine& p) { return ext_is_identity(ext_mul(p, kJubJubOrder)); }
+
+// on the curve and in the prime-order subgroup; the last point that passed is remembered (a circuit
+// appends the same constant point over and over: benches/plonk.rs does so once per loop iteration)
+static bool jj_is_valid_subgroup_point(const JubJubAffine& p) {
+  static thread_local JubJubAffine last_ok;
+  static thread_local bool have = false;
+  if (have && last_ok == p) return true;
+  if (!jj_is_on_curve(p) || !jj_is_torsion_free(p)) return false;
+  last_ok = p;
+  have = true;
+  return true;
+}
 
 static bool lt_order(const uint64_t k[4]) {
   for (int i = 3; i >= 0; i--) {
@@ -164,11 +251,23 @@ Witness Composer::append_witness(const Fr& v) {
 void Composer::append_custom_gate(const Constraint& c) {
   for (int k = 0; k < 4; k++)
     if (c.w[k] >= witnesses_.size()) throw ComposerError{PB200_ERR_INVALID_ARG, "gate wired to an unallocated witness"};
+  if (c.has_pi) public_inputs_[n_gates_] = c.pi;
+  n_gates_++;
+  if (witness_only_) return;
   Gate g;
   memcpy(g.q, c.q, sizeof g.q);
   memcpy(g.w, c.w, sizeof g.w);
-  if (c.has_pi) public_inputs_[gates_.size()] = c.pi;
   gates_.push_back(g);
+}
+
+void Composer::set_witness_only(bool on) {
+  if (!on && witness_only_ && n_gates_ != gates_.size())
+    throw ComposerError{PB200_ERR_INVALID_ARG, "gates appended in witness-only mode are not stored"};
+  witness_only_ = on;
+  if (on) {
+    gates_.clear();
+    gates_.shrink_to_fit();
+  }
 }
 
 void Composer::append_gate(Constraint c) {
@@ -179,7 +278,12 @@ void Composer::append_gate(Constraint c) {
 // Solves q_M a b + q_L a + q_R b + q_O c + q_F d + q_C + PI = 0 for c (composer.rs:298-352)
 bool Composer::append_evaluated_output(Constraint s, Witness* out) {
   const Fr a = (*this)[s.w[0]], b = (*this)[s.w[1]], d = (*this)[s.w[3]];
-  const Fr x = s.q[Q_M] * a * b + s.q[Q_L] * a + s.q[Q_R] * b + s.q[Q_F] * d + s.q[Q_C] + (s.has_pi ? s.pi : Fr::zero());
+  Fr x = s.q[Q_C];
+  if (s.has_pi) x = x + s.pi;
+  if (!s.q[Q_M].is_zero()) add_term(x, s.q[Q_M], a * b);
+  add_term(x, s.q[Q_L], a);
+  add_term(x, s.q[Q_R], b);
+  add_term(x, s.q[Q_F], d);
   const Fr& y = s.q[Q_O];
   bool solved = true;
   Fr c;
@@ -292,12 +396,11 @@ void Composer::range_check_even(Witness witness, unsigned num_bits) {
   const unsigned pad = 1 + (((num_quads << 1) - num_bits) >> 1);
   std::vector<Constraint> rows(num_gates + 1, with(Q_RANGE, Fr::one()));
   static const int wire_of[4] = {3, 2, 1, 0};  // D, C, B, A
-  const Fr four = fr_u64(4);
   Fr acc = Fr::zero();
   Witness last = ZERO;
   for (unsigned i = pad; i <= num_quads; i++) {
     const unsigned bit_index = (num_quads - i) << 1;
-    acc = acc * four + fr_u64((uint64_t)bits[bit_index] + 2u * bits[bit_index + 1]);
+    acc = acc.dbl().dbl() + fr_u64((uint64_t)bits[bit_index] + 2u * bits[bit_index + 1]);
     last = append_witness(acc);
     rows[i / 4].w[wire_of[i % 4]] = last;
   }
@@ -317,16 +420,15 @@ Witness Composer::logic_component(Witness a, Witness b, unsigned bit_pairs, bool
   fr_to_bits((*this)[b], bbits);
   Constraint row = with(Q_LOGIC, is_xor ? minus_one() : Fr::one());
   row.constant(is_xor ? minus_one() : Fr::one());
-  const Fr four = fr_u64(4);
   Fr left_acc = Fr::zero(), right_acc = Fr::zero(), out_acc = Fr::zero();
   for (unsigned i = 0; i < bit_pairs; i++) {
     const unsigned hi = num_bits - 1 - 2 * i;  // quads from the most significant pair down
     const unsigned lq = (abits[hi] << 1) | abits[hi - 1];
     const unsigned rq = (bbits[hi] << 1) | bbits[hi - 1];
     const unsigned oq = is_xor ? (lq ^ rq) : (lq & rq);
-    left_acc = left_acc * four + fr_u64(lq);
-    right_acc = right_acc * four + fr_u64(rq);
-    out_acc = out_acc * four + fr_u64(oq);
+    left_acc = left_acc.dbl().dbl() + fr_u64(lq);
+    right_acc = right_acc.dbl().dbl() + fr_u64(rq);
+    out_acc = out_acc.dbl().dbl() + fr_u64(oq);
     const Witness wit_a = append_witness(left_acc);
     const Witness wit_b = append_witness(right_acc);
     const Witness wit_c = append_witness(fr_u64(lq * rq));
@@ -421,7 +523,7 @@ WitnessPoint Composer::append_point(const JubJubAffine& p) {
 }
 
 WitnessPoint Composer::append_constant_point(const JubJubAffine& p) {
-  if (!jj_is_on_curve(p) || !jj_is_torsion_free(p)) throw ComposerError{PB200_ERR_JUBJUB_POINT, "JubJubPointNotTorsionFree"};
+  if (!jj_is_valid_subgroup_point(p)) throw ComposerError{PB200_ERR_JUBJUB_POINT, "JubJubPointNotTorsionFree"};
   const Witness x = append_constant(p.u);
   const Witness y = append_constant(p.v);
   return {x, y};
@@ -474,9 +576,11 @@ WitnessPoint Composer::component_sub_point(WitnessPoint a, WitnessPoint b) { ret
 WitnessPoint Composer::component_add_point(WitnessPoint a, WitnessPoint b) { return add_point_gates(a, b); }
 
 // One curve-addition gate pair: (x1, y1, x2, y2) then (x3, y3, -, x1 y2) (point.rs:266-312)
-WitnessPoint Composer::add_point_gates(WitnessPoint a, WitnessPoint b) {
+WitnessPoint Composer::add_point_gates(WitnessPoint a, WitnessPoint b) { return add_point_gates(a, b, jj_add(point_value(a), point_value(b))); }
+
+// ... with the sum already known (chains compute their sums in extended coordinates, one inversion in all)
+WitnessPoint Composer::add_point_gates(WitnessPoint a, WitnessPoint b, const JubJubAffine& sum) {
   const JubJubAffine p1 = point_value(a), p2 = point_value(b);
-  const JubJubAffine sum = jj_add(p1, p2);
   const Witness x1y2 = append_witness(p1.u * p2.v);
   const Witness x3 = append_witness(sum.u);
   const Witness y3 = append_witness(sum.v);
@@ -505,11 +609,27 @@ WitnessPoint Composer::component_select_point(Witness bit, WitnessPoint a, Witne
 // Double-and-add over the 252 scalar bits, most significant first (point.rs:361-378)
 WitnessPoint Composer::component_mul_point(Witness jubjub, WitnessPoint p) {
   const std::vector<Witness> bits = component_decomposition(jubjub, 252);
-  WitnessPoint result = IDENTITY;
+  // the values of the whole chain first (extended coordinates, one inversion), then the gates
+  const JubJubExt pe = ext_from_affine(point_value(p));
+  std::vector<JubJubExt> chain;
+  chain.reserve(2 * bits.size());
+  JubJubExt r = ext_identity();
   for (size_t k = bits.size(); k-- > 0;) {
-    result = add_point_gates(result, result);
+    r = ext_add(r, r);
+    chain.push_back(r);
+    // select_identity: bit ? P : identity (the bits are boolean-constrained witnesses of a decomposition);
+    // adding the identity leaves the point as it is
+    if (!(*this)[bits[k]].is_zero()) r = ext_add(r, pe);
+    chain.push_back(r);
+  }
+  std::vector<JubJubAffine> vals;
+  ext_batch_to_affine(chain, vals);
+  WitnessPoint result = IDENTITY;
+  size_t j = 0;
+  for (size_t k = bits.size(); k-- > 0;) {
+    result = add_point_gates(result, result, vals[j++]);
     const WitnessPoint addend = select_identity_gates(bits[k], p);
-    result = add_point_gates(result, addend);
+    result = add_point_gates(result, addend, vals[j++]);
   }
   return result;
 }
@@ -529,8 +649,18 @@ void Composer::assert_canonical_jubjub_scalar(Witness scalar) {
 // 256 signed-digit rounds against the precomputed multiples 2^(255-i) G (fixed_base.rs:47-226)
 WitnessPoint Composer::component_mul_generator(Witness jubjub, const JubJubAffine& generator) {
   constexpr int kRounds = 256, kLeadingZeroRounds = 256 - (252 + 1);
-  if (!jj_is_on_curve(generator) || !jj_is_torsion_free(generator) || generator == jj_identity())
-    throw ComposerError{PB200_ERR_JUBJUB_GENERATOR, "JubJubGeneratorNotPrimeOrder"};
+  // multiples[i] = 2^(255-i) G: a table per generator, validated and built once per thread and generator
+  static thread_local JubJubAffine table_gen;
+  static thread_local std::vector<JubJubAffine> multiples;
+  if (multiples.empty() || !(table_gen == generator)) {
+    if (!jj_is_on_curve(generator) || !jj_is_torsion_free(generator) || generator == jj_identity())
+      throw ComposerError{PB200_ERR_JUBJUB_GENERATOR, "JubJubGeneratorNotPrimeOrder"};
+    std::vector<JubJubExt> dbl(kRounds);
+    dbl[kRounds - 1] = ext_from_affine(generator);
+    for (int i = kRounds - 2; i >= 0; i--) dbl[i] = ext_add(dbl[i + 1], dbl[i + 1]);
+    ext_batch_to_affine(dbl, multiples);
+    table_gen = generator;
+  }
   const Fr canonical = (*this)[jubjub].from_mont();
   if (!lt_order(canonical.v)) throw ComposerError{PB200_ERR_JUBJUB_SCALAR, "JubJubScalarMalformed"};
   int8_t digits[256];
@@ -538,14 +668,10 @@ WitnessPoint Composer::component_mul_generator(Witness jubjub, const JubJubAffin
 
   assert_canonical_jubjub_scalar(jubjub);
 
-  std::vector<JubJubAffine> multiples(kRounds);  // multiples[i] = 2^(255-i) G
-  multiples[kRounds - 1] = generator;
-  for (int i = kRounds - 2; i >= 0; i--) multiples[i] = jj_add(multiples[i + 1], multiples[i + 1]);
-
   std::vector<Fr> scalar_acc(kRounds + 1), xy_alpha(kRounds);
-  std::vector<JubJubAffine> point_acc(kRounds + 1);
+  std::vector<JubJubExt> point_ext(kRounds + 1);
   scalar_acc[0] = Fr::zero();
-  point_acc[0] = jj_identity();
+  point_ext[0] = ext_identity();
   for (int i = 0; i < kRounds; i++) {
     const int8_t digit = digits[kRounds - 1 - i];
     Fr s_add = Fr::zero();
@@ -558,9 +684,11 @@ WitnessPoint Composer::component_mul_generator(Witness jubjub, const JubJubAffin
       p_add = jj_neg(multiples[i]);
     }
     scalar_acc[i + 1] = scalar_acc[i].dbl() + s_add;
-    point_acc[i + 1] = jj_add(point_acc[i], p_add);
-    xy_alpha[i] = p_add.u * p_add.v;
+    point_ext[i + 1] = digit ? ext_add(point_ext[i], ext_from_affine(p_add)) : point_ext[i];
+    xy_alpha[i] = digit ? p_add.u * p_add.v : Fr::zero();
   }
+  std::vector<JubJubAffine> point_acc;
+  ext_batch_to_affine(point_ext, point_acc);
 
   Witness leading = ZERO;
   for (int i = 0; i < kRounds; i++) {
@@ -864,6 +992,10 @@ int pb200_jubjub_mul(const uint64_t* point_uv, const uint64_t* scalar, uint64_t*
   memcpy(out_uv + 4, r.v.v, 32);
   return PB200_OK;
 }
+int pb200_composer_set_witness_only(pb200_composer_t* c, int on) {
+  PBC_REQUIRE(c);
+  return guarded([&] { c->c.set_witness_only(on != 0); });
+}
 int pb200_composer_bench_circuit(pb200_composer_t* c, size_t degree) {
   PBC_REQUIRE(c);
   return guarded([&] { c->c.bench_circuit(degree); });
@@ -871,6 +1003,10 @@ int pb200_composer_bench_circuit(pb200_composer_t* c, size_t degree) {
 int pb200_composer_export(const pb200_composer_t* c, uint64_t* selectors, uint32_t* wires, uint64_t* witnesses, uint64_t* pi_idx,
                           uint64_t* pi_vals) {
   PBC_REQUIRE(c);
+  if ((selectors || wires) && c->c.witness_only()) {
+    pb::g_last_error = "a witness-only composer holds no gate layout (export selectors / wires from the composer the prover was compiled from)";
+    return PB200_ERR_INVALID_ARG;
+  }
   const std::vector<pbc::Gate>& gates = c->c.gates();
   const size_t n = gates.size();
   for (size_t i = 0; i < n; i++) {

@@ -94,7 +94,12 @@ class Composer {
 
   Composer();  // Composer::initialized: constants 0, 1 and the two dummy gates
 
-  size_t constraints() const { return gates_.size(); }
+  size_t constraints() const { return n_gates_; }
+  // Witness-only mode (the composer of Prover::prove, src/compiler/prover.rs:425: the circuit is re-run for
+  // its witness values and public inputs; the gate layout is the one the prover was compiled from): gates
+  // are validated and counted but not stored.
+  void set_witness_only(bool on);
+  bool witness_only() const { return witness_only_; }
   size_t n_witnesses() const { return witnesses_.size(); }
   const Fr& operator[](Witness w) const;
   const std::vector<Gate>& gates() const { return gates_; }
@@ -149,6 +154,8 @@ class Composer {
 
  private:
   std::vector<Gate> gates_;
+  size_t n_gates_ = 0;
+  bool witness_only_ = false;
   std::vector<Fr> witnesses_;
   std::map<size_t, Fr> public_inputs_;
 
@@ -159,6 +166,7 @@ class Composer {
   void assert_canonical_truncation(Witness high, Witness low, unsigned num_bits);
   void assert_canonical_jubjub_scalar(Witness scalar);
   WitnessPoint add_point_gates(WitnessPoint a, WitnessPoint b);
+  WitnessPoint add_point_gates(WitnessPoint a, WitnessPoint b, const JubJubAffine& sum);
   WitnessPoint select_identity_gates(Witness bit, WitnessPoint a);
   JubJubAffine point_value(WitnessPoint p) const;
 };

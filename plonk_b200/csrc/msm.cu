@@ -39,7 +39,12 @@ namespace pb {
 
 static constexpr int kGroup = 8;
 static constexpr unsigned kClassChunk = 512;  // members of a class summed by one warp
-static constexpr unsigned kHeavy = 512;  // buckets longer than this many size units (~8x the average) get a whole CTA  // buckets per running-sum group in the reduction
+// Buckets longer than kHeavy size units (the unit is chosen so that the average bucket of a dense MSM is
+// 32..64 units, i.e. > 2.5x .. 5x the average) leave the one-thread-group-per-bucket kernel: they are cut
+// into chunks of kHeavyChunk entries, one warp per chunk, and the chunk sums are added per bucket afterwards.
+// A lane of k_msm_accumulate therefore never walks more than kHeavy << size_shift >> log_split entries.
+static constexpr unsigned kHeavy = 160;
+static constexpr unsigned kHeavyChunk = 256;
 
 PB_D G1Affine ld_affine(const uint4* p, size_t i) {
   const uint4* q = p + 6 * i;
@@ -259,9 +264,10 @@ __global__ void k_msm_digits(const uint4* scalars, size_t n, size_t stride, int 
 // clipped size), so that the threads of a warp in k_msm_accumulate get buckets of near-equal length
 // and the warp does not idle on its longest lane.
 __global__ void __launch_bounds__(1024) k_msm_scan(const unsigned* counts, unsigned* offsets, unsigned* order, unsigned* n_heavy,
-                                                   unsigned nb, int size_shift) {
+                                                   unsigned* heavy_pre, unsigned nb, int size_shift) {
   __shared__ unsigned sums[1024];
   __shared__ unsigned bins[1024];
+  __shared__ unsigned s_nh;
   const unsigned b = blockIdx.x, tid = threadIdx.x;
   const unsigned* cnt = counts + (size_t)b * nb;
   unsigned* off = offsets + (size_t)b * (nb + 1);
@@ -300,12 +306,37 @@ __global__ void __launch_bounds__(1024) k_msm_scan(const unsigned* counts, unsig
   }
   bins[tid] = sums[tid] - mine;  // exclusive start of each bin
   // buckets are ordered largest first, so the heavy ones are order[0 .. n_heavy)
-  if (tid == 1022u - kHeavy) n_heavy[b] = sums[tid];  // bins 0 .. 1022-kHeavy hold the sizes > kHeavy
+  if (tid == 1022u - kHeavy) {  // bins 0 .. 1022-kHeavy hold the sizes > kHeavy
+    n_heavy[b] = sums[tid];
+    s_nh = sums[tid];
+  }
   __syncthreads();
   for (unsigned k = tid; k < nb; k += 1024) {
     const unsigned pos = atomicAdd(&bins[1023u - min(cnt[k] >> size_shift, 1023u)], 1u);
     ord[pos] = k;
   }
+  __syncthreads();  // ord[0 .. n_heavy) is complete (written by this CTA)
+  // heavy_pre[h] = number of kHeavyChunk-entry chunks of the heavy buckets before the h-th one
+  const unsigned nh = s_nh;
+  unsigned* hp = heavy_pre + (size_t)b * (nb + 1);
+  const unsigned per = (nh + 1023u) / 1024u;
+  const unsigned h_lo = min(nh, tid * per), h_hi = min(nh, h_lo + per);
+  unsigned c = 0;
+  for (unsigned h = h_lo; h < h_hi; h++) c += (cnt[ord[h]] + kHeavyChunk - 1) / kHeavyChunk;
+  sums[tid] = c;
+  __syncthreads();
+  for (unsigned d = 1; d < 1024; d <<= 1) {
+    unsigned v = (tid >= d) ? sums[tid - d] : 0;
+    __syncthreads();
+    sums[tid] += v;
+    __syncthreads();
+  }
+  unsigned run2 = sums[tid] - c;
+  for (unsigned h = h_lo; h < h_hi; h++) {
+    hp[h] = run2;
+    run2 += (cnt[ord[h]] + kHeavyChunk - 1) / kHeavyChunk;
+  }
+  if (tid == 1023) hp[nh] = sums[1023];
 }
 
 __global__ void k_msm_scatter(const unsigned* ebkt, const unsigned* epos, const unsigned* offsets, size_t n,
@@ -344,7 +375,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_msm_accumulate(const uint
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned split = 1u << log_split;
   const unsigned b = blockIdx.y;
-  // the first n_heavy buckets of `order` are handled by k_msm_accumulate_heavy
+  // the first n_heavy buckets of `order` are handled by k_msm_heavy_chunks
   const bool valid = t < ((size_t)nb << log_split) && (t >> log_split) >= n_heavy[b];
   const unsigned part = (unsigned)t & (split - 1);
   unsigned bucket = 0, lo = 0, hi = 0;
@@ -384,43 +415,67 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_msm_accumulate(const uint
   if (valid && part == 0) st_xyzz(sums, (size_t)b * nb + bucket, acc);
 }
 
-// Buckets longer than kHeavy (skewed scalars: many equal coefficients, 0/1 vectors, ...): one CTA per
-// bucket, strided over its entries, then a CTA-wide tree.  With uniformly random scalars n_heavy is 0
-// and the CTAs exit at once.
-__global__ void __launch_bounds__(128) k_msm_accumulate_heavy(const uint4* table, const unsigned* sorted, const unsigned* offsets,
-                                                              const unsigned* order, const unsigned* n_heavy, unsigned nb, size_t cap,
-                                                              uint4* sums) {
-  __shared__ uint4 sh[4 * 12];
+PB_D G1Xyzz warp_sum(G1Xyzz v) {
+  for (int d = 16; d > 0; d >>= 1) {
+    G1Xyzz o = shfl_down_xyzz(v, d, 32);
+    xyzz_add(v, o);
+  }
+  return v;
+}
+
+// Heavy buckets (skewed scalars: many equal coefficients, 0/1 vectors, the wire VALUES of a circuit, whose
+// small entries pile tens of thousands of points onto digits 1, 2, 3 of the lowest window): the chunks of
+// all heavy buckets form one work list, a warp per chunk of kHeavyChunk entries (8 mixed additions per lane
+// and a shuffle tree), so a 30 000-entry bucket is spread over 118 warps instead of being walked by one CTA.
+// With uniformly random scalars there is no heavy bucket and the warps exit at once.
+__global__ void __launch_bounds__(128) k_msm_heavy_chunks(const uint4* table, const unsigned* sorted, const unsigned* offsets,
+                                                          const unsigned* order, const unsigned* n_heavy, const unsigned* heavy_pre,
+                                                          unsigned nb, size_t cap, size_t part_cap, uint4* partials) {
   const unsigned b = blockIdx.y;
   const unsigned nh = n_heavy[b];
+  if (nh == 0) return;
+  const unsigned* hp = heavy_pre + (size_t)b * (nb + 1);
+  const unsigned total = hp[nh];
   const unsigned* src = sorted + (size_t)b * cap;
   const unsigned* off = offsets + (size_t)b * (nb + 1);
-  for (unsigned h = blockIdx.x; h < nh; h += gridDim.x) {
-    const unsigned bucket = order[(size_t)b * nb + h];
-    const unsigned start = off[bucket], end = off[bucket + 1];
+  const unsigned* ord = order + (size_t)b * nb;
+  const unsigned lane = threadIdx.x & 31, warps = gridDim.x * 4;
+  for (unsigned v = blockIdx.x * 4 + (threadIdx.x >> 5); v < total; v += warps) {
+    unsigned lo = 0, hi = nh;  // the heavy bucket h with hp[h] <= v < hp[h + 1]
+    while (hi - lo > 1) {
+      const unsigned mid = (lo + hi) >> 1;
+      if (hp[mid] <= v) lo = mid; else hi = mid;
+    }
+    const unsigned bucket = ord[lo];
+    const unsigned start = off[bucket] + (v - hp[lo]) * kHeavyChunk, end = min(off[bucket + 1], start + kHeavyChunk);
     G1Xyzz acc = G1Xyzz::identity();
-    for (unsigned k = start + threadIdx.x; k < end; k += 128) {
+    for (unsigned k = start + lane; k < end; k += 32) {
       const unsigned e = __ldg(src + k);
       G1Affine p = ld_affine(table, e >> 1);
       if (p.is_inf()) continue;
       if (e & 1u) p.y = p.y.neg();
       xyzz_madd(acc, p.x, p.y);
     }
-    for (int d = 16; d > 0; d >>= 1) {
-      G1Xyzz o = shfl_down_xyzz(acc, d, 32);
-      xyzz_add(acc, o);
+    acc = warp_sum(acc);
+    if (lane == 0) st_xyzz(partials, (size_t)b * part_cap + v, acc);
+  }
+}
+
+// ... and the chunk sums of each heavy bucket are added by one warp.
+__global__ void __launch_bounds__(128) k_msm_heavy_combine(const uint4* partials, const unsigned* order, const unsigned* n_heavy,
+                                                           const unsigned* heavy_pre, unsigned nb, size_t part_cap, uint4* sums) {
+  const unsigned b = blockIdx.y;
+  const unsigned nh = n_heavy[b];
+  const unsigned* hp = heavy_pre + (size_t)b * (nb + 1);
+  const unsigned lane = threadIdx.x & 31, warps = gridDim.x * 4;
+  for (unsigned h = blockIdx.x * 4 + (threadIdx.x >> 5); h < nh; h += warps) {
+    G1Xyzz acc = G1Xyzz::identity();
+    for (unsigned v = hp[h] + lane; v < hp[h + 1]; v += 32) {
+      G1Xyzz q = ld_xyzz(partials, (size_t)b * part_cap + v);
+      xyzz_add(acc, q);
     }
-    if ((threadIdx.x & 31) == 0) st_xyzz(sh, threadIdx.x >> 5, acc);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      G1Xyzz r = ld_xyzz(sh, 0);
-      for (int w = 1; w < 4; w++) {
-        G1Xyzz o = ld_xyzz(sh, w);
-        xyzz_add(r, o);
-      }
-      st_xyzz(sums, (size_t)b * nb + bucket, r);
-    }
-    __syncthreads();
+    acc = warp_sum(acc);
+    if (lane == 0) st_xyzz(sums, (size_t)b * nb + order[(size_t)b * nb + h], acc);
   }
 }
 
@@ -460,14 +515,6 @@ __global__ void __launch_bounds__(64) k_msm_groups(const uint4* sums, unsigned n
   }
   st_xyzz(S, (size_t)b * n_groups + G, run);
   st_xyzz(A, (size_t)b * n_groups + G, acc);
-}
-
-PB_D G1Xyzz warp_sum(G1Xyzz v) {
-  for (int d = 16; d > 0; d >>= 1) {
-    G1Xyzz o = shfl_down_xyzz(v, d, 32);
-    xyzz_add(v, o);
-  }
-  return v;
 }
 
 // One warp per (class, chunk of kClassChunk members); 4 warps per CTA.  out is [batch][nclasses][chunks].
@@ -582,6 +629,22 @@ __global__ void k_imad_peak(unsigned* out, int iters, unsigned seed) {
   if (x == 0x1234567ull) out[0] = (unsigned)x;  // never true in practice: keeps the chain alive
 }
 
+// Throughput probe of the carry-chained Fp product itself: every thread runs a dependent chain of
+// products (x <- x * y), 1024 threads per SM-slot, so the multiply pipe is saturated by independent
+// chains of different warps exactly as in the bucket kernels.  Gives the ceiling the G1 kernels are
+// measured against (Fp products per second).
+__global__ void __launch_bounds__(256) k_fp_product_peak(uint4* out, int iters, unsigned seed) {
+  Fp x = Fp::one(), y = Fp::r2();
+  x.v[0] ^= (threadIdx.x * 2654435761u + seed) & 0xffffu;  // still < p: only low bits change
+  y.v[1] ^= (blockIdx.x * 40503u) & 0xffffu;
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
+    x = x * y;
+    y = y * x;
+  }
+  if (x.is_zero() && y.is_zero()) st_fp(out, x);  // never true: keeps the chain alive
+}
+
 // ---------------------------------------------------------------------------------------------
 // Optional in-library timing of the dominant kernel (bucket accumulation) with CUDA events on the
 // launching stream; read by bench.py for the roofline line.
@@ -609,18 +672,73 @@ static void xyzz_dev_to_host(const uint32_t* w, pbh::HXyzz* o) {
   memcpy(o->zzz.v, w + 36, 48);
 }
 
-int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_t n, uint32_t batch,
-            size_t stride, uint64_t* out_affine_host, cudaStream_t st, Arena* ar) {
-  if (first + n > srs->n_points) return fail(PB200_ERR_DEGREE_TOO_LARGE, "more scalars than commit-key points");
-  if (batch == 0) return 0;
-  if (n == 0) {
-    memset(out_affine_host, 0, (size_t)batch * 96);
-    return 0;
+// What the host needs to finish an MSM whose kernels have been enqueued: the digit plan of the bucket
+// reduction.  It depends on the window width of the key only, never on the number of scalars, so the
+// ranks of a point-sharded MSM (pb200_msm_g1_allgather*) share it as long as their slices use the same c.
+struct MsmTail {
+  DigitPlan plan;
+  int log_g = 0;
+  int c = 0;
+  uint32_t batch = 0;
+  size_t words_per_entry() const { return (size_t)(plan.ndig + 1) * 48; }  // 32-bit words of one batch entry
+};
+
+static int msm_plan_c(int c, uint32_t batch, MsmTail* tail, unsigned* n_groups_out, int* g_out) {
+  const unsigned nb = 1u << (c - 1);
+  const int g = std::min<unsigned>(kGroup, nb);
+  const unsigned n_groups = nb / g;
+  int log_g = 0;
+  while ((1 << log_g) < g) log_g++;
+  DigitPlan& plan = tail->plan;
+  int total_bits = 0;
+  while ((1u << total_bits) < n_groups) total_bits++;
+  plan.ndig = (total_bits + 3) / 4;
+  if (plan.ndig > 7) return fail(PB200_ERR_INVALID_ARG, "window too wide for the bucket reduction");
+  int sh = 0, cls = 0;
+  for (int j = 0; j < plan.ndig; j++) {
+    const int bits = (total_bits - sh) / (plan.ndig - j);  // spread evenly, low digits first
+    plan.shift[j] = sh;
+    plan.bits[j] = bits;
+    plan.first_class[j] = cls;
+    sh += bits;
+    cls += 1 << bits;
   }
+  plan.n_digit_classes = cls;
+  plan.n_a_classes = (int)((n_groups + 255) / 256);
+  plan.nclasses = plan.n_digit_classes + plan.n_a_classes;
+  tail->log_g = log_g;
+  tail->c = c;
+  tail->batch = batch;
+  *n_groups_out = n_groups;
+  *g_out = g;
+  return 0;
+}
+static int msm_plan(const pb200_srs* srs, uint32_t batch, MsmTail* tail, unsigned* n_groups_out, int* g_out) {
+  return msm_plan_c(srs->c, batch, tail, n_groups_out, g_out);
+}
+
+// Enqueues every kernel of `batch` MSMs over the points [first, first + n) of the key on `st`.  The
+// digit sums land in *d_result ([batch][ndig + 1] XYZZ points, carved from `scope`, so they live until
+// the scope is released); nothing is synchronised.  n == 0 yields identities.
+static int msm_enqueue(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_t n, uint32_t batch, size_t stride,
+                       cudaStream_t st, ScratchScope& scope, uint4** d_result, MsmTail* tail, cudaEvent_t* prof_ev,
+                       const unsigned** d_totals) {
+  if (first + n > srs->n_points) return fail(PB200_ERR_DEGREE_TOO_LARGE, "more scalars than commit-key points");
   const int c = srs->c, W = srs->W;
   const unsigned nb = 1u << (c - 1);
   const size_t cap = n * (size_t)W;
   if (((srs->n_points * (size_t)W) << 1) >= ((size_t)1 << 32)) return fail(PB200_ERR_INVALID_ARG, "commit key too large for 32-bit point references");
+  unsigned n_groups = 0;
+  int g = 0;
+  PB_TRY(msm_plan(srs, batch, tail, &n_groups, &g));
+  const DigitPlan& plan = tail->plan;
+  uint4* result = nullptr;
+  PB_ALLOC(scope, result, (size_t)batch * (plan.ndig + 1) * 192);
+  *d_result = result;
+  if (n == 0) {
+    PB_CUDA(cudaMemsetAsync(result, 0, (size_t)batch * (plan.ndig + 1) * 192, st));
+    return 0;
+  }
 
   // threads per bucket: enough CTAs to fill the machine, but at least ~8 points per thread
   int log_split = 0;
@@ -629,38 +747,15 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
     while (log_split < 5 && ((size_t)nb * batch << log_split) < (1u << 17) && (avg >> (log_split + 1)) >= 8) log_split++;
     if (const char* env = getenv("PB200_MSM_LOG_SPLIT")) log_split = atoi(env);
   }
-  const int g = std::min<unsigned>(kGroup, nb);
-  const unsigned n_groups = nb / g;
-  int log_g = 0;
-  while ((1 << log_g) < g) log_g++;
-  DigitPlan plan;
-  {
-    int total_bits = 0;
-    while ((1u << total_bits) < n_groups) total_bits++;
-    plan.ndig = (total_bits + 3) / 4;
-    int sh = 0, cls = 0;
-    for (int j = 0; j < plan.ndig; j++) {
-      const int bits = (total_bits - sh) / (plan.ndig - j);  // spread evenly, low digits first
-      plan.shift[j] = sh;
-      plan.bits[j] = bits;
-      plan.first_class[j] = cls;
-      sh += bits;
-      cls += 1 << bits;
-    }
-    plan.n_digit_classes = cls;
-    plan.n_a_classes = (int)((n_groups + 255) / 256);
-    plan.nclasses = plan.n_digit_classes + plan.n_a_classes;
-    if (plan.ndig > 7) return fail(PB200_ERR_INVALID_ARG, "window too wide for the bucket reduction");
-  }
 
-  ScratchScope scope(ar, st);
   unsigned *counts = nullptr, *offsets = nullptr, *order = nullptr, *ebkt = nullptr, *epos = nullptr, *sorted = nullptr;
-  uint4 *sums = nullptr, *classes = nullptr, *S = nullptr, *A = nullptr, *result = nullptr;
+  uint4 *sums = nullptr, *classes = nullptr, *S = nullptr, *A = nullptr;
   PB_ALLOC(scope, counts, (size_t)batch * nb * 4);
   PB_ALLOC(scope, offsets, (size_t)batch * (nb + 1) * 4);
   PB_ALLOC(scope, order, (size_t)batch * nb * 4);
-  unsigned* n_heavy = nullptr;
+  unsigned *n_heavy = nullptr, *heavy_pre = nullptr;
   PB_ALLOC(scope, n_heavy, (size_t)batch * 4);
+  PB_ALLOC(scope, heavy_pre, (size_t)batch * (nb + 1) * 4);
   PB_ALLOC(scope, ebkt, (size_t)batch * cap * 4);
   PB_ALLOC(scope, epos, (size_t)batch * cap * 4);
   PB_ALLOC(scope, sorted, (size_t)batch * cap * 4);
@@ -670,23 +765,20 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
   PB_ALLOC(scope, classes, (size_t)batch * plan.nclasses * chunks * 192);
   PB_ALLOC(scope, S, (size_t)batch * n_groups * 192);
   PB_ALLOC(scope, A, (size_t)batch * n_groups * 192);
-  PB_ALLOC(scope, result, (size_t)batch * (plan.ndig + 1) * 192);
   PB_CUDA(cudaMemsetAsync(counts, 0, (size_t)batch * nb * 4, st));
 
   PB_LAUNCH(k_msm_digits, dim3(div_up(n, 128), batch), 128, 0, st, (const uint4*)d_scalars, n, stride, c, W, nb,
             counts, ebkt, epos);
   int size_shift = 0;  // size unit: average bucket ~ 64 units
   while (((cap / nb) >> size_shift) > 64) size_shift++;
-  PB_LAUNCH(k_msm_scan, batch, 1024, 0, st, counts, offsets, order, n_heavy, nb, size_shift);
+  // chunk sums of the heavy buckets: at most cap / kHeavyChunk full chunks plus one ragged chunk per heavy bucket
+  const size_t part_cap = cap / kHeavyChunk + cap / ((size_t)kHeavy << size_shift) + 2;
+  uint4* partials = nullptr;
+  PB_ALLOC(scope, partials, (size_t)batch * part_cap * 192);
+  PB_LAUNCH(k_msm_scan, batch, 1024, 0, st, counts, offsets, order, n_heavy, heavy_pre, nb, size_shift);
   PB_LAUNCH(k_msm_scatter, dim3(div_up(n, 256), W, batch), 256, 0, st, ebkt, epos, offsets, n, W, nb,
             srs->n_points, first, sorted);
-  const bool prof = g_prof_on.load(std::memory_order_relaxed) != 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  if (prof) {
-    PB_CUDA(cudaEventCreate(&ev0));
-    PB_CUDA(cudaEventCreate(&ev1));
-    PB_CUDA(cudaEventRecord(ev0, st));
-  }
+  if (prof_ev) PB_CUDA(cudaEventRecord(prof_ev[0], st));
   {
     // CTA shape: 64 threads x 4 CTAs/SM and 128 x 2 hold the same 8 warps per SM (register-limited);
     // the smaller CTA balances the tail of the launch better when there are few waves.  Forcing 12 or
@@ -704,25 +796,120 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
       PB_LAUNCH((k_msm_accumulate<128, 2>), grid, 128, 0, st, srs->table, sorted, offsets, order, n_heavy, nb, log_split, cap, sums);
     }
   }
-  std::vector<unsigned> h_tot(batch, 0);
-  if (prof) {
-    PB_CUDA(cudaEventRecord(ev1, st));
-    PB_CUDA(cudaMemcpy2DAsync(h_tot.data(), 4, offsets + nb, (size_t)(nb + 1) * 4, 4, batch, cudaMemcpyDeviceToHost, st));
-  }
-  PB_LAUNCH(k_msm_accumulate_heavy, dim3(64, batch), 128, 0, st, srs->table, sorted, offsets, order, n_heavy, nb, cap, sums);
+  if (d_totals) *d_totals = offsets + nb;  // offsets[b][nb] = the entries of batch b (stride nb + 1)
+  PB_LAUNCH(k_msm_heavy_chunks, dim3(592, batch), 128, 0, st, srs->table, sorted, offsets, order, n_heavy, heavy_pre, nb, cap, part_cap, partials);
+  PB_LAUNCH(k_msm_heavy_combine, dim3(64, batch), 128, 0, st, (const uint4*)partials, order, n_heavy, heavy_pre, nb, part_cap, sums);
+  if (prof_ev) PB_CUDA(cudaEventRecord(prof_ev[1], st));  // the bucket-accumulation phase: every entry has been added once
   PB_LAUNCH(k_msm_groups, dim3(div_up(n_groups, 64), batch), 64, 0, st, (const uint4*)sums, nb, g, S, A);
   PB_LAUNCH(k_msm_group_classes, dim3(div_up(plan.nclasses, 4), batch, chunks), 128, 0, st, (const uint4*)S, (const uint4*)A,
             n_groups, plan, chunks, classes);
   PB_LAUNCH(k_msm_final, batch, 256, 0, st, (const uint4*)classes, plan, chunks, result);
   PB_CUDA(cudaGetLastError());
-  const size_t host_words = (size_t)batch * (plan.ndig + 1) * 48;
+  return 0;
+}
+
+// Host tail.  `host` holds n_parts x batch entries of (ndig + 1) XYZZ points (part-major): the digit
+// sums of n_parts partial MSMs that share one plan (n_parts = 1 for an ordinary MSM, the rank count for a
+// point-sharded one).  R = sum A_G + g * sum_j 2^shift_j D_j is linear in the D_j and in sum A_G, so
+// the parts are added digit by digit first and one Horner over the digits follows; then the affine
+// normalisation of Commitment::from (commitment.rs:89-93) with one shared inversion per batch
+// (Montgomery's trick over the ZZ*ZZZ of the batch's results).
+static void msm_finish(const uint32_t* host, const MsmTail& tail, int n_parts, uint64_t* out_affine_host) {
+  const DigitPlan& plan = tail.plan;
+  const uint32_t batch = tail.batch;
+  const size_t wpe = tail.words_per_entry();
+  std::vector<pbh::HXyzz> res(batch);
+  for (uint32_t b = 0; b < batch; b++) {
+    auto digit = [&](int d) {
+      pbh::HXyzz s = pbh::HXyzz::identity(), t;
+      for (int p = 0; p < n_parts; p++) {
+        xyzz_dev_to_host(host + ((size_t)p * batch + b) * wpe + (size_t)d * 48, &t);
+        pbh::hxyzz_add(s, t);
+      }
+      return s;
+    };
+    pbh::HXyzz h = pbh::HXyzz::identity();
+    for (int d = plan.ndig - 1; d >= 0; d--) {
+      pbh::HXyzz t = digit(d);
+      pbh::hxyzz_add(h, t);
+      const int dbl = d > 0 ? plan.bits[d - 1] : tail.log_g;
+      for (int k = 0; k < dbl; k++) h = pbh::hxyzz_dbl(h);
+    }
+    pbh::HXyzz t = digit(plan.ndig);
+    pbh::hxyzz_add(h, t);
+    res[b] = h;
+  }
+  std::vector<pbh::HFp> den(batch), pre(batch);
+  pbh::HFp acc = pbh::HFp::one();
+  for (uint32_t b = 0; b < batch; b++) {
+    den[b] = res[b].is_inf() ? pbh::HFp::one() : res[b].zz * res[b].zzz;
+    pre[b] = acc;
+    acc = acc * den[b];
+  }
+  pbh::HFp inv = acc.inv();
+  for (uint32_t b = batch; b-- > 0;) {
+    const pbh::HFp i = inv * pre[b];  // 1 / (zz * zzz)
+    inv = inv * den[b];
+    pbh::HFp x = pbh::HFp::zero(), y = pbh::HFp::zero();
+    if (!res[b].is_inf()) {
+      x = res[b].x * (i * res[b].zzz);
+      y = res[b].y * (i * res[b].zz);
+    }
+    memcpy(out_affine_host + (size_t)b * 12, x.v, 48);
+    memcpy(out_affine_host + (size_t)b * 12 + 6, y.v, 48);
+  }
+}
+
+// The host tail on its own (pb200_msm_combine_parts): digit sums of n_parts partial MSMs -> affine results.
+int msm_combine_parts(const uint32_t* parts, int n_parts, int window_bits, uint32_t batch, uint64_t* out_affine_host, size_t* words_per_entry) {
+  MsmTail tail;
+  unsigned n_groups = 0;
+  int g = 0;
+  PB_TRY(msm_plan_c(window_bits, batch, &tail, &n_groups, &g));
+  if (words_per_entry) *words_per_entry = tail.words_per_entry();
+  if (parts && out_affine_host) msm_finish(parts, tail, n_parts, out_affine_host);
+  return 0;
+}
+
+int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_t n, uint32_t batch,
+            size_t stride, uint64_t* out_affine_host, cudaStream_t st, Arena* ar) {
+  if (first + n > srs->n_points) return fail(PB200_ERR_DEGREE_TOO_LARGE, "more scalars than commit-key points");
+  if (batch == 0) return 0;
+  if (n == 0) {
+    memset(out_affine_host, 0, (size_t)batch * 96);
+    return 0;
+  }
+  const bool prof = g_prof_on.load(std::memory_order_relaxed) != 0;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  struct EvGuard {
+    cudaEvent_t* e;
+    ~EvGuard() {
+      for (int i = 0; i < 2; i++)
+        if (e[i]) cudaEventDestroy(e[i]);
+    }
+  } ev_guard{ev};
+  if (prof) {
+    PB_CUDA(cudaEventCreate(&ev[0]));
+    PB_CUDA(cudaEventCreate(&ev[1]));
+  }
+  ScratchScope scope(ar, st);
+  uint4* result = nullptr;
+  MsmTail tail;
+  const unsigned* d_totals = nullptr;
+  PB_TRY(msm_enqueue(srs, first, d_scalars, n, batch, stride, st, scope, &result, &tail, prof ? ev : nullptr, &d_totals));
+  std::vector<unsigned> h_tot(batch, 0);
+  if (prof) {
+    const unsigned nb = 1u << (srs->c - 1);
+    PB_CUDA(cudaMemcpy2DAsync(h_tot.data(), 4, d_totals, (size_t)(nb + 1) * 4, 4, batch, cudaMemcpyDeviceToHost, st));
+  }
+  const size_t host_words = (size_t)batch * tail.words_per_entry();
   uint32_t* host = (uint32_t*)pinned_scratch(host_words * 4);
   if (!host) return fail(PB200_ERR_CUDA, "pinned staging buffer");
   PB_CUDA(cudaMemcpyAsync(host, result, host_words * 4, cudaMemcpyDeviceToHost, st));
   PB_CUDA(stream_wait(st));
   if (prof) {
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) {
+    if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) {
       uint64_t adds = 0;
       for (unsigned t : h_tot) adds += t;
       g_prof_acc_ns.fetch_add((uint64_t)(ms * 1e6));
@@ -730,49 +917,83 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
       g_prof_acc_points.fetch_add((uint64_t)n * batch);
       g_prof_acc_launches.fetch_add(1);
     }
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
   }
   scope.release();  // the stream was synchronised above: the scratch is dead
+  msm_finish(host, tail, 1, out_affine_host);
+  return 0;
+}
 
-  // Host tail: R = sum A_G + g * sum_j 2^shift_j D_j (Horner over the digits), then the affine
-  // normalisation of Commitment::from (commitment.rs:89-93) with one shared inversion per batch
-  // (Montgomery's trick over the ZZ*ZZZ of the batch's results).
-  std::vector<pbh::HXyzz> res(batch);
-  for (uint32_t b = 0; b < batch; b++) {
-    const uint32_t* hp = host + (size_t)b * (plan.ndig + 1) * 48;
-    pbh::HXyzz h = pbh::HXyzz::identity(), t;
-    for (int d = plan.ndig - 1; d >= 0; d--) {
-      xyzz_dev_to_host(hp + (size_t)d * 48, &t);
-      pbh::hxyzz_add(h, t);
-      const int dbl = d > 0 ? plan.bits[d - 1] : log_g;
-      for (int k = 0; k < dbl; k++) h = pbh::hxyzz_dbl(h);
-    }
-    xyzz_dev_to_host(hp + (size_t)plan.ndig * 48, &t);
-    pbh::hxyzz_add(h, t);
-    res[b] = h;
-  }
+// ---- point-sharded MSM: slice MSM -> ONE ncclAllGather of the digit sums -> local sum (SURVEY.md
+// section 8e-ii, BASELINE configs[3]).  The gather runs on device buffers on the MSM's own stream,
+// straight behind the reduction kernels: there is one host synchronisation per call.  Every rank's
+// record starts with a 16-byte header {status, c, ndig, batch}; a rank whose local part failed still
+// joins the collective with status != 0, so its peers return an error instead of hanging.
+typedef int (*nccl_all_gather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
+int msm_allgather(const pb200_srs* srs, const uint64_t* scalars, bool scalars_on_device, size_t n, uint32_t batch, size_t stride,
+                  nccl_all_gather_fn all_gather, void* comm, int n_ranks, int* nccl_rc, uint64_t* out_affine_host, cudaStream_t st) {
+  MsmTail tail;
+  unsigned n_groups = 0;
+  int g = 0;
+  PB_TRY(msm_plan(srs, batch, &tail, &n_groups, &g));
+  const size_t payload = (size_t)batch * tail.words_per_entry() * 4, rec = 16 + payload;
+  ScratchScope scope(nullptr, st);
+  uint8_t *d_send = nullptr, *d_recv = nullptr;
+  PB_ALLOC(scope, d_send, rec);
+  PB_ALLOC(scope, d_recv, rec * (size_t)n_ranks);
+  uint8_t* host = (uint8_t*)pinned_scratch(rec * (size_t)n_ranks + 16);
+  if (!host) return fail(PB200_ERR_CUDA, "pinned staging buffer");
+  uint32_t* hdr = (uint32_t*)(host + rec * (size_t)n_ranks);  // staging for this rank's header
+  // local part; from here on every path reaches the collective
+  int local_rc = 0;
   {
-    std::vector<pbh::HFp> den(batch), pre(batch);
-    pbh::HFp acc = pbh::HFp::one();
-    for (uint32_t b = 0; b < batch; b++) {
-      den[b] = res[b].is_inf() ? pbh::HFp::one() : res[b].zz * res[b].zzz;
-      pre[b] = acc;
-      acc = acc * den[b];
+    uint4* result = nullptr;
+    MsmTail t2;
+    const uint64_t* d_scalars = scalars;
+    if (!scalars_on_device && n) {
+      uint64_t* d = (uint64_t*)scope.take((size_t)batch * n * 32);
+      cudaError_t e = d ? cudaMemcpy2DAsync(d, n * 32, scalars, stride * 32, n * 32, batch, cudaMemcpyHostToDevice, st) : cudaErrorMemoryAllocation;
+      if (e != cudaSuccess) local_rc = fail(PB200_ERR_CUDA, "scalar upload", cudaGetErrorString(e));
+      d_scalars = d;
+      stride = n;
     }
-    pbh::HFp inv = acc.inv();
-    for (uint32_t b = batch; b-- > 0;) {
-      const pbh::HFp i = inv * pre[b];  // 1 / (zz * zzz)
-      inv = inv * den[b];
-      pbh::HFp x = pbh::HFp::zero(), y = pbh::HFp::zero();
-      if (!res[b].is_inf()) {
-        x = res[b].x * (i * res[b].zzz);
-        y = res[b].y * (i * res[b].zz);
-      }
-      memcpy(out_affine_host + (size_t)b * 12, x.v, 48);
-      memcpy(out_affine_host + (size_t)b * 12 + 6, y.v, 48);
+    if (local_rc == 0) local_rc = msm_enqueue(srs, 0, d_scalars, n, batch, stride, st, scope, &result, &t2, nullptr, nullptr);
+    cudaError_t e = cudaSuccess;
+    if (local_rc == 0) e = cudaMemcpyAsync(d_send + 16, result, payload, cudaMemcpyDeviceToDevice, st);
+    if (local_rc != 0 || e != cudaSuccess) {
+      if (local_rc == 0) local_rc = fail(PB200_ERR_CUDA, "partial result copy", cudaGetErrorString(e));
+      cudaMemsetAsync(d_send + 16, 0, payload, st);
     }
   }
+  const std::string local_msg = g_last_error;
+  hdr[0] = local_rc ? 1u : 0u;
+  hdr[1] = (uint32_t)tail.c;
+  hdr[2] = (uint32_t)tail.plan.ndig;
+  hdr[3] = batch;
+  cudaError_t e = cudaMemcpyAsync(d_send, hdr, 16, cudaMemcpyHostToDevice, st);
+  *nccl_rc = 0;
+  if (e == cudaSuccess) *nccl_rc = all_gather(d_send, d_recv, rec, /*ncclUint8*/ 1, comm, st);
+  if (e == cudaSuccess && *nccl_rc == 0) e = cudaMemcpyAsync(host, d_recv, rec * (size_t)n_ranks, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && *nccl_rc == 0) e = stream_wait(st);
+  if (*nccl_rc != 0) return fail(PB200_ERR_CUDA, "ncclAllGather");
+  PB_CUDA(e);
+  scope.release();
+  if (local_rc != 0) {
+    g_last_error = local_msg;
+    return local_rc;
+  }
+  std::vector<uint32_t> parts((size_t)n_ranks * payload / 4);
+  for (int r = 0; r < n_ranks; r++) {
+    const uint32_t* h = (const uint32_t*)(host + rec * (size_t)r);
+    if (h[0] != 0) {
+      char msg[48];
+      snprintf(msg, sizeof msg, "rank %d", r);
+      return fail(PB200_ERR_CUDA, "the partial MSM of another rank failed", msg);
+    }
+    if (h[1] != (uint32_t)tail.c || h[2] != (uint32_t)tail.plan.ndig || h[3] != batch)
+      return fail(PB200_ERR_INVALID_ARG, "ranks disagree on the MSM window or batch (key slices must use one window width)");
+    memcpy(parts.data() + (size_t)r * payload / 4, h + 4, payload);
+  }
+  msm_finish(parts.data(), tail, n_ranks, out_affine_host);
   return 0;
 }
 
@@ -781,7 +1002,12 @@ size_t msm_workspace_bytes(const pb200_srs* srs, size_t n, uint32_t batch) {
   const size_t nb = (size_t)1 << (srs->c - 1), cap = n * (size_t)srs->W;
   const size_t n_groups = std::max<size_t>(1, nb / kGroup);
   size_t b = 0;
-  b += 3 * ((size_t)batch * (nb + 1) * 4 + 256);      // counts, offsets, order
+  b += 4 * ((size_t)batch * (nb + 1) * 4 + 256);      // counts, offsets, order, heavy_pre
+  {
+    int size_shift = 0;
+    while (((cap / nb) >> size_shift) > 64) size_shift++;
+    b += (size_t)batch * (cap / kHeavyChunk + cap / ((size_t)kHeavy << size_shift) + 2) * 192 + 256;  // partials
+  }
   b += (size_t)batch * 4 + 256;                        // n_heavy
   b += 3 * ((size_t)batch * cap * 4 + 256);            // ebkt, epos, sorted
   b += (size_t)batch * nb * 192 + 256;                 // sums
@@ -791,12 +1017,12 @@ size_t msm_workspace_bytes(const pb200_srs* srs, size_t n, uint32_t batch) {
   return b + 4096;
 }
 
-int srs_upload(const uint8_t* raw, size_t n_points, pb200_srs** out) {
+int srs_upload(const uint8_t* raw, size_t n_points, pb200_srs** out, int window_bits) {
   if (n_points == 0) return fail(PB200_ERR_INVALID_ARG, "empty commit key");
   cudaStream_t st = thread_stream();
   pb200_srs* s = new pb200_srs();
   s->n_points = n_points;
-  s->c = pick_window(n_points);
+  s->c = window_bits ? window_bits : pick_window(n_points);
   s->W = (256 + s->c - 1) / s->c;
   s->table = nullptr;
   cudaError_t e = cudaMalloc((void**)&s->table, (size_t)s->W * n_points * 96);
@@ -817,6 +1043,8 @@ int srs_upload(const uint8_t* raw, size_t n_points, pb200_srs** out) {
   *out = s;
   return 0;
 }
+
+int srs_upload(const uint8_t* raw, size_t n_points, pb200_srs** out) { return srs_upload(raw, n_points, out, 0); }
 
 // The key's points as uploaded (window 0 of the table), n_points affine points on the device.
 const uint4* srs_points(const pb200_srs* s) { return s->table; }
@@ -956,10 +1184,36 @@ int imad_peak(double* out) {
   return 0;
 }
 
+int fp_product_peak(double* out) {
+  cudaStream_t st = thread_stream();
+  uint4* d;
+  PB_CUDA(cudaMalloc((void**)&d, 48));
+  cudaDeviceProp prop;
+  int dev;
+  PB_CUDA(cudaGetDevice(&dev));
+  PB_CUDA(cudaGetDeviceProperties(&prop, dev));
+  const int blocks = prop.multiProcessorCount * 4, threads = 256, iters = 400;
+  PB_LAUNCH(k_fp_product_peak, blocks, threads, 0, st, d, 20, 1u);
+  cudaEvent_t e0, e1;
+  PB_CUDA(cudaEventCreate(&e0));
+  PB_CUDA(cudaEventCreate(&e1));
+  PB_CUDA(cudaEventRecord(e0, st));
+  PB_LAUNCH(k_fp_product_peak, blocks, threads, 0, st, d, iters, 2u);
+  PB_CUDA(cudaEventRecord(e1, st));
+  PB_CUDA(cudaStreamSynchronize(st));
+  float ms = 0;
+  PB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  *out = (double)blocks * threads * iters * 2.0 / (ms * 1e-3);
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  return 0;
+}
+
 }  // namespace pb
 
 namespace pb {
 size_t srs_len(const pb200_srs* s) { return s->n_points; }
+int srs_window(const pb200_srs* s) { return s->c; }
+int msm_window_for(size_t n_points) { return pick_window(n_points ? n_points : 1); }
 void srs_free(pb200_srs* s) {
   cudaFree(s->table);
   delete s;

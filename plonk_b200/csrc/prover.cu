@@ -37,6 +37,9 @@ size_t msm_workspace_bytes(const pb200_srs* srs, size_t n, uint32_t batch);
 int srs_upload(const uint8_t* raw, size_t n_points, pb200_srs** out);
 void srs_free(pb200_srs* s);
 size_t srs_len(const pb200_srs* s);
+const uint4* srs_points(const pb200_srs* s);
+int srs_from_device(const uint4* d_points, size_t n_points, pb200_srs** out);
+int lagrange_key_dev(const uint4* d_in, int log_n, uint4* d_out, cudaStream_t st);
 int get_twiddles(int logm, bool inverse, cudaStream_t st, const uint4** out);
 int fill_powers(uint4* out, size_t n, const Fr& base, const Fr& scale, cudaStream_t st);
 Fr ntt_group_gen(int log_n, bool inverse);
@@ -94,6 +97,15 @@ struct BlindArgs {
   int nb;
   int npoly;
 };
+// Scalars of the blinder terms of a Lagrange-basis wire commitment: blinding adds b_k X^k (X^n - 1), so
+// after the n wire values come -b_0, -b_1 (against [1]G, [x]G) and b_0, b_1 (against [x^n]G, [x^(n+1)]G).
+__global__ void k_lagrange_tail(uint4* sc, size_t stride, size_t n, BlindArgs a) {
+  const int t = threadIdx.x;
+  if (t >= 2 * a.npoly) return;
+  const int p = t >> 1, k = t & 1;
+  stg_fr(sc, (size_t)p * stride + n + k, a.b[p][k].neg());
+  stg_fr(sc, (size_t)p * stride + n + 2 + k, a.b[p][k]);
+}
 __global__ void k_blind(uint4* polys, size_t stride, size_t n, BlindArgs a) {
   const int t = threadIdx.x;
   if (t >= a.npoly * a.nb) return;
@@ -331,18 +343,22 @@ PB_D Q widget_var(const WidgetCh& s, const Q& ed, const WireVals& v) {  // curve
   return (xy + x3c + y3c) * ch;
 }
 
-__global__ void __launch_bounds__(128) k_quotient(QuotArgs q) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= q.n8) return;
-  const size_t n8 = q.n8, iw = (i + 8) & (n8 - 1);
+// One point of the quotient.  The six witness rows (z, a, b, c, d, pi) have stride `ws` and are read at
+// column i, the "next row" values (X -> omega X) at column iw; the prover-key tables (stride n8),
+// the point itself, L_1 and 1/Z_H are read at index ki of the 8n coset; the result goes to out[oi].
+//   8n coset (the reference's schedule): ws = 8n, iw = i + 8 mod 8n, ki = oi = i
+//   4n coset (its even points):          ws = 4n, iw = i + 4 mod 4n, ki = 2i, oi = i
+//   single points (Horner-evaluated):    ws = 16, iw = i + 8,        ki = 1 + n i, oi = i
+PB_D void quotient_point(const QuotArgs& q, size_t ws, size_t i, size_t iw, size_t ki, size_t oi) {
+  const size_t n8 = q.n8;
   WireVals v;
   const Q z = ldg_fr(q.w8, i), z_w = ldg_fr(q.w8, iw);
-  v.a = ldg_fr(q.w8, n8 + i); v.a_w = ldg_fr(q.w8, n8 + iw);
-  v.b = ldg_fr(q.w8, 2 * n8 + i); v.b_w = ldg_fr(q.w8, 2 * n8 + iw);
-  v.c = ldg_fr(q.w8, 3 * n8 + i);
-  v.d = ldg_fr(q.w8, 4 * n8 + i); v.d_w = ldg_fr(q.w8, 4 * n8 + iw);
-  const Q pi = ldg_fr(q.w8, 5 * n8 + i);
-#define KEY(k) ldg_fr(q.key8, (size_t)(k) * n8 + i)
+  v.a = ldg_fr(q.w8, ws + i); v.a_w = ldg_fr(q.w8, ws + iw);
+  v.b = ldg_fr(q.w8, 2 * ws + i); v.b_w = ldg_fr(q.w8, 2 * ws + iw);
+  v.c = ldg_fr(q.w8, 3 * ws + i);
+  v.d = ldg_fr(q.w8, 4 * ws + i); v.d_w = ldg_fr(q.w8, 4 * ws + iw);
+  const Q pi = ldg_fr(q.w8, 5 * ws + i);
+#define KEY(k) ldg_fr(q.key8, (size_t)(k) * n8 + ki)
   const Q q_l = KEY(Q_L), q_r = KEY(Q_R), q_c = KEY(Q_C);
   // arithmetic/proverkey.rs:44-69
   Q t = (v.a * v.b * KEY(Q_M) + v.a * q_l + v.b * q_r + v.c * KEY(Q_O) + v.d * KEY(Q_F) + q_c) * KEY(Q_ARITH);
@@ -352,7 +368,7 @@ __global__ void __launch_bounds__(128) k_quotient(QuotArgs q) {
   if (q.has_var) t = t + widget_var(q.ch_var, q.edwards_d, v) * KEY(Q_VAR);
   t = t + pi;
   // permutation/proverkey.rs:40-125
-  const Q x = ldg_fr(q.linear8, i);
+  const Q x = ldg_fr(q.linear8, ki);
   const Q alpha = q.alpha, beta = q.beta, gamma = q.gamma;
   const Q bx = beta * x;
   Q ident = (v.a + bx + gamma) * (v.b + mul_small(bx, 7) + gamma) * (v.c + mul_small(bx, 13) + gamma) *
@@ -360,9 +376,29 @@ __global__ void __launch_bounds__(128) k_quotient(QuotArgs q) {
   Q copy = (v.a + beta * KEY(S1) + gamma) * (v.b + beta * KEY(S2) + gamma) * (v.c + beta * KEY(S3) + gamma) *
            (v.d + beta * KEY(S4) + gamma) * z_w * alpha;
 #undef KEY
-  Q l1 = Q(ldg_fr(q.l1_8, i)) * Q(q.alpha_sq);
+  Q l1 = Q(ldg_fr(q.l1_8, ki)) * Q(q.alpha_sq);
   t = t + ident - copy + (z - Q::one()) * l1;
-  stg_fr(q.out, i, (t * Q(q.vh_inv[i & 7])).v);
+  stg_fr(q.out, oi, (t * Q(q.vh_inv[ki & 7])).v);
+}
+
+__global__ void __launch_bounds__(128) k_quotient(QuotArgs q) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= q.n8) return;
+  quotient_point(q, q.n8, i, (i + 8) & (q.n8 - 1), i, i);
+}
+// The same on the 4n coset g*H_4n = the even points of the 8n coset (PB200_QUOT4N=1, see prove_dev).
+__global__ void __launch_bounds__(128) k_quotient_4n(QuotArgs q) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n4 = q.n8 >> 1;
+  if (i >= n4) return;
+  quotient_point(q, n4, i, (i + 4) & (n4 - 1), 2 * i, i);
+}
+// ... and at the eight odd points 1 + n k of the 8n coset, the witness values coming from Horner
+// evaluations laid out as [6][16] (columns 0..7: x_k, columns 8..15: omega x_k).
+__global__ void __launch_bounds__(128) k_quotient_pts(QuotArgs q) {
+  const size_t k = threadIdx.x;
+  if (k >= 8) return;
+  quotient_point(q, 16, k, k + 8, 1 + (q.n8 >> 3) * k, k);
 }
 
 // flag |= any nonzero element in p[lo, hi)
@@ -434,6 +470,70 @@ __global__ void k_sum_rows(const uint4* partial, unsigned nblocks, uint4* out) {
   stg_fr(out, j, acc);
 }
 
+// The same for one set of points and several polynomials laid out with a fixed stride: job (y, z) evaluates
+// base + z * row_stride at point[y]; partial is [z][y][nblocks].
+struct EvalRows {
+  const uint4* base;
+  size_t row_stride;  // elements
+  unsigned len;
+  Fr point[16];
+};
+__global__ void __launch_bounds__(256) k_poly_eval_rows(EvalRows jobs, uint4* partial, unsigned nblocks) {
+  __shared__ uint4 sh[256][2];
+  const int tid = threadIdx.x;
+  const size_t base = ((size_t)blockIdx.x * 256 + tid) * 8;
+  const uint4* poly = jobs.base + 2 * (size_t)blockIdx.z * jobs.row_stride;
+  const unsigned len = jobs.len;
+  Fr acc = Fr::zero();
+  if (base < len) {
+    const Fr x = jobs.point[blockIdx.y];
+#pragma unroll
+    for (int k = 7; k >= 0; k--) {
+      Fr c = (base + k < len) ? ld_fr_plain(poly, base + k) : Fr::zero();
+      acc = acc * x + c;
+    }
+    acc = acc * x.pow_u64(base);
+  }
+  sh[tid][0] = make_uint4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
+  sh[tid][1] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
+  __syncthreads();
+  for (int d = 128; d > 0; d >>= 1) {
+    if (tid < d) {
+      Fr v = lds_pair(sh[tid]) + lds_pair(sh[tid + d]);
+      sh[tid][0] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
+      sh[tid][1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) stg_fr(partial, ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * nblocks + blockIdx.x, lds_pair(sh[0]));
+}
+
+// Step 3 + 4 of the 4n-coset quotient (see prove_dev): thread j < 8 computes
+//   t_hi[j] = (h^-j / 8) * sum_k e_k w8^(-jk),   e_k = (t(x_k) - u(x_k)) / (-2 g^4n),
+// then patches t's coefficients j and 4n + j (j < 7); a non-zero t_hi[7] raises `flag`.
+struct Quot4nFix {
+  Fr c;             // 1 / (-2 g^4n)
+  Fr g4n;
+  Fr hinv8[8];      // h^-j / 8
+  Fr w8inv_pow[8];  // w8^-m
+};
+__global__ void k_quot4n_fix(const uint4* tx, const uint4* ux, uint4* tcoef, size_t n4, Quot4nFix f, unsigned* flag) {
+  const int j = threadIdx.x;
+  if (j >= 8) return;
+  Fr acc = Fr::zero();
+  for (int k = 0; k < 8; k++) {
+    const Fr e = (ld_fr_plain(tx, k) - ld_fr_plain(ux, k)) * f.c;
+    acc = acc + e * f.w8inv_pow[(j * k) & 7];
+  }
+  const Fr t_hi = acc * f.hinv8[j];
+  if (j == 7) {
+    if (!t_hi.is_zero()) atomicOr(flag, 1u);
+    return;
+  }
+  stg_fr(tcoef, j, ld_fr_plain(tcoef, j) - f.g4n * t_hi);
+  stg_fr(tcoef, n4 + j, t_hi);
+}
+
 // out[i] = sum_k coef[k] * poly[k][i]
 struct LinArgs {
   const uint4* poly[24];
@@ -468,6 +568,11 @@ __global__ void k_scale_period8(uint4* p, size_t n, Period8 c) {
   if (i < n) stg_fr(p, i, ld_fr_plain(p, i) * c.c[i & 7]);
 }
 
+struct Quot4nConsts {
+  Fr xs[16];  // x_k = h w8^k (k < 8), then omega x_k
+  Quot4nFix fix;
+};
+
 }  // namespace pb
 
 // ---------------------------------------------------------------------------------------------
@@ -480,6 +585,9 @@ struct pb200_prover {
   size_t constraints = 0, n = 0, n8 = 0;
   int log_n = 0;
   pb200_srs* srs = nullptr;
+  // (unless PB200_LAGRANGE=0) [L_0(x)]G .. [L_{n-1}(x)]G, then [1]G, [x]G, [x^n]G, [x^(n+1)]G - the wire polynomials
+  // are committed through their values (short scalars) plus the two blinder terms
+  pb200_srs* srs_lag = nullptr;
   uint32_t* d_wires = nullptr;  // [4][constraints]
   uint4* d_polys = nullptr;     // [15][n]
   uint4* d_key8 = nullptr;      // [15][8n]
@@ -487,6 +595,8 @@ struct pb200_prover {
   uint4* d_l1_8 = nullptr;      // [8n]
   uint4* d_sigma = nullptr;     // [4][n]
   HFr vh_inv[8];
+  pb::Fr edwards_d;       // dusk_jubjub::EDWARDS_D, Montgomery form
+  pb::Quot4nConsts q4;    // constants of the 4n-coset quotient (round 3)
   int has_widget[4] = {0, 0, 0, 0};
   uint8_t comm[pb::N_POLY][48];
   size_t n_witnesses = 0;
@@ -511,6 +621,8 @@ static HFr to_host(const Fr& x) {
 }
 static HFr hfr_pow(const HFr& x, uint64_t e) { return x.pow(&e, 1); }
 
+// Exclusive scan of n elements: CTA-local scans of 2048 elements, the scan of the CTA totals (by the same
+// routine, so any length works: 2^22 + 8 elements are 2049 totals, two levels), then the fix-up.
 template <bool MUL, bool REV>
 static int fr_scan(const uint4* in, size_t n, uint4* out, cudaStream_t st, Arena* ar) {
   const unsigned nblk = div_up(n, 2048);
@@ -520,8 +632,7 @@ static int fr_scan(const uint4* in, size_t n, uint4* out, cudaStream_t st, Arena
   PB_ALLOC(scope, tot_scan, (size_t)nblk * 32);
   PB_LAUNCH((k_scan_local<MUL, REV>), nblk, 256, 0, st, in, n, out, tot);
   if (nblk > 1) {
-    if (nblk > 2048) return fail(PB200_ERR_INVALID_ARG, "scan too large");
-    PB_LAUNCH((k_scan_local<MUL, false>), 1, 256, 0, st, (const uint4*)tot, (size_t)nblk, tot_scan, (uint4*)nullptr);
+    PB_TRY((fr_scan<MUL, false>((const uint4*)tot, (size_t)nblk, tot_scan, st, ar)));
     PB_LAUNCH((k_scan_fixup<MUL, REV>), div_up(n, 256), 256, 0, st, out, n, (const uint4*)tot_scan);
   }
   PB_CUDA(cudaGetLastError());
@@ -565,6 +676,27 @@ static int prover_build(pb200_prover* P, const uint8_t* label, size_t label_len,
   P->log_n = log_n;
   if (log_n + 3 >= 32) return fail(PB200_ERR_INVALID_DOMAIN, "quotient domain too large");
   PB_TRY(srs_upload(srs_raw, keep + 1, &P->srs));
+  {
+    static const bool lagrange_env = [] {
+      const char* e = getenv("PB200_LAGRANGE");
+      return !e || atoi(e) != 0;
+    }();
+    if (lagrange_env && n >= 2 && keep + 1 >= n + 2) {
+      uint4* comb = nullptr;  // n Lagrange points + 4 monomial ones
+      PB_CUDA(cudaMalloc((void**)&comb, (n + 4) * 96));
+      const uint4* mono = srs_points(P->srs);
+      int rc = lagrange_key_dev(mono, log_n, comb, st);
+      const size_t idx[4] = {0, 1, n, n + 1};
+      cudaError_t e = cudaSuccess;
+      for (int k = 0; k < 4 && e == cudaSuccess; k++)
+        e = cudaMemcpyAsync(comb + 6 * (n + k), mono + 6 * idx[k], 96, cudaMemcpyDeviceToDevice, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (rc == 0 && e == cudaSuccess) rc = srs_from_device(comb, n + 4, &P->srs_lag);
+      cudaFree(comb);
+      PB_TRY(rc);
+      PB_CUDA(e);
+    }
+  }
   const size_t n8 = P->n8;
   PB_CUDA(cudaMalloc((void**)&P->d_wires, 4 * constraints * 4));
   PB_CUDA(cudaMalloc((void**)&P->d_polys, (size_t)N_POLY * n * 32));
@@ -646,6 +778,27 @@ static int prover_build(pb200_prover* P, const uint8_t* label, size_t label_len,
     PB_LAUNCH(k_batch_div, div_up(div_up(n8, 8), 128), 128, 0, st, (const uint4*)nullptr, (const uint4*)P->d_l1_8, n8, P->d_l1_8);
     PB_LAUNCH(k_scale_period8, div_up(n8, 256), 256, 0, st, P->d_l1_8, n8, c);
   }
+  {  // per-domain constants of round 3, computed once (each costs a host-side inversion or power)
+    P->edwards_d = to_dev((HFr::from_u64(10240) * HFr::from_u64(10241).inv()).neg());
+    const HFr g = to_host(ntt_coset_gen(false)), w8n = to_host(ntt_group_gen(log_n + 3, false));
+    const uint64_t e_n[1] = {(uint64_t)n}, e_4n[1] = {(uint64_t)(4 * n)};
+    const HFr h = g * w8n, w8r = w8n.pow(e_n, 1), wn = to_host(ntt_group_gen(log_n, false)), g4n = g.pow(e_4n, 1);
+    HFr xs[16];
+    xs[0] = h;
+    for (int k = 1; k < 8; k++) xs[k] = xs[k - 1] * w8r;
+    for (int k = 0; k < 8; k++) xs[8 + k] = xs[k] * wn;
+    for (int k = 0; k < 16; k++) P->q4.xs[k] = to_dev(xs[k]);
+    P->q4.fix.c = to_dev((g4n.dbl().neg()).inv());
+    P->q4.fix.g4n = to_dev(g4n);
+    const HFr h_inv = h.inv(), w8i = w8r.inv();
+    HFr hj = HFr::from_u64(8).inv(), wp = HFr::one();
+    for (int j = 0; j < 8; j++) {
+      P->q4.fix.hinv8[j] = to_dev(hj);
+      P->q4.fix.w8inv_pow[j] = to_dev(wp);
+      hj = hj * h_inv;
+      wp = wp * w8i;
+    }
+  }
   // sigma evaluations over n (prover.rs:95-100)
   PB_TRY(ntt_run((const uint64_t*)(P->d_polys + 2 * (size_t)S1 * n), n, (uint64_t*)P->d_sigma, log_n, 0, 0, 4, n, n, st, nullptr));
   PB_CUDA(cudaGetLastError());
@@ -654,7 +807,8 @@ static int prover_build(pb200_prover* P, const uint8_t* label, size_t label_len,
     const size_t stride = n + 8;
     const size_t elems = 8 * n + 16 * stride + 64 * n + 64 + 16 * (size_t)div_up(stride, 2048) + 4 * (size_t)div_up(stride, 2048);
     const size_t ntt_tmp = 6 * n8 * 32;
-    const size_t msm_ws = msm_workspace_bytes(P->srs, std::min(stride, srs_len(P->srs)), 4);
+    size_t msm_ws = msm_workspace_bytes(P->srs, std::min(stride, srs_len(P->srs)), 4);
+    if (P->srs_lag) msm_ws = std::max(msm_ws, msm_workspace_bytes(P->srs_lag, n + 4, 4));
     P->ws_bytes = elems * 32 + std::max(ntt_tmp, msm_ws) + (size_t)64 * 256 + (1 << 20);
   }
   return 0;
@@ -676,6 +830,7 @@ int prover_new(const uint8_t* label, size_t label_len, size_t constraints, const
 void prover_free(pb200_prover* P) {
   if (!P) return;
   if (P->srs) srs_free(P->srs);
+  if (P->srs_lag) srs_free(P->srs_lag);
   cudaFree(P->d_wires); cudaFree(P->d_polys); cudaFree(P->d_key8); cudaFree(P->d_linear8); cudaFree(P->d_l1_8); cudaFree(P->d_sigma);
   for (char* w : P->ws_all) cudaFree(w);
   delete P;
@@ -700,8 +855,11 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
   const HFr* BL = (const HFr*)blinders_host;
   pbh::Transcript tr = base_transcript(P);
   const HFr* PIV = (const HFr*)pi_vals;
+  if (n_pi && (!pi_idx || !pi_vals)) return fail(PB200_ERR_INVALID_ARG, "public inputs announced but not given");
   for (size_t i = 0; i < n_pi; i++) {
     if (pi_idx[i] >= P->constraints) return fail(PB200_ERR_INVALID_ARG, "public input index out of range");
+    // the reference keeps public inputs in a BTreeMap keyed by gate index (composer.rs:465-480): ascending, no duplicates
+    if (i && pi_idx[i] <= pi_idx[i - 1]) return fail(PB200_ERR_INVALID_ARG, "public input positions must be strictly increasing");
     tr.append_scalar("pi", PIV[i]);
   }
   const uint4* w_half = nullptr;
@@ -779,7 +937,21 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
       for (int i = 0; i < 2; i++) ba.b[p][i] = to_dev(BL[2 * p + i]);
     PB_LAUNCH(k_blind, 1, 32, 0, st, wp, stride, n, ba);
   }
-  PB_TRY(msm_run(P->srs, 0, (const uint64_t*)wp, n + 2, 4, stride, aff, st, ar));
+  if (P->srs_lag) {
+    // the same four group elements from the wire VALUES: sum_i w_i [L_i(x)]G + b_0 ([x^n]G - [1]G) +
+    // b_1 ([x^(n+1)]G - [x]G); w8 is free until round 3 and stages the scalars
+    uint4* sc = w8;
+    PB_CUDA(cudaMemcpy2DAsync(sc, stride * 32, wv, n * 32, n * 32, 4, cudaMemcpyDeviceToDevice, st));
+    BlindArgs ba;
+    ba.nb = 2;
+    ba.npoly = 4;
+    for (int p = 0; p < 4; p++)
+      for (int i = 0; i < 2; i++) ba.b[p][i] = to_dev(BL[2 * p + i]);
+    PB_LAUNCH(k_lagrange_tail, 1, 32, 0, st, sc, stride, n, ba);
+    PB_TRY(msm_run(P->srs_lag, 0, (const uint64_t*)sc, n + 4, 4, stride, aff, st, ar));
+  } else {
+    PB_TRY(msm_run(P->srs, 0, (const uint64_t*)wp, n + 2, 4, stride, aff, st, ar));
+  }
   for (int k = 0; k < 4; k++) compress_affine(aff + 12 * k, c48[k]);
   tr.append_commitment("a_comm", c48[0]);
   tr.append_commitment("b_comm", c48[1]);
@@ -811,12 +983,20 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
   const HFr ch_logic = tr.challenge_scalar("logic separation challenge");
   const HFr ch_fixed = tr.challenge_scalar("fixed base separation challenge");
   const HFr ch_var = tr.challenge_scalar("variable base separation challenge");
-  // coset evaluations of z, a, b, c, d and the public-input polynomial in one batch
-  // (quotient_poly.rs:50-59, 177)
-  PB_TRY(ntt_run((const uint64_t*)zp, n + 3, (uint64_t*)w8, log_n + 3, 0, 1, n_pi ? 6 : 5, stride, n8, st, ar));
-  if (!n_pi) PB_CUDA(cudaMemsetAsync(w8 + 2 * 5 * n8, 0, n8 * 32, st));  // empty PI polynomial: 8n zeros
+  // t(X) has at most 4n + 7 coefficients, so the six coset transforms, the pointwise pass and the
+  // inverse transform run on the 4n coset (the even points of the 8n one) and the top seven coefficients
+  // are recovered from eight further points; the algebra is validated against the oracle in
+  // tests/models/quotient_4n_model.py.  PB200_QUOT4N=0 restores the reference's 8n schedule
+  // (quotient_poly.rs:50-137), which the parity suite keeps running as well.
+  static const bool quot4n_env = [] {
+    const char* e = getenv("PB200_QUOT4N");
+    return !e || atoi(e) != 0;
+  }();
+  const bool quot4n = quot4n_env && n >= 16;  // the small arrays of step 2 live in the upper half of w8
+  const size_t n4 = 4 * n;
+  size_t t_len = n8;  // coefficients of t(X) present in tcoef
+  QuotArgs q;
   {
-    QuotArgs q;
     q.w8 = w8; q.key8 = P->d_key8; q.linear8 = P->d_linear8; q.l1_8 = P->d_l1_8; q.out = quot; q.n8 = n8;
     q.alpha = to_dev(alpha); q.beta = to_dev(beta); q.gamma = to_dev(gamma); q.alpha_sq = to_dev(alpha.sqr());
     auto powers = [](const HFr& ch) {
@@ -826,21 +1006,70 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
       return w;
     };
     q.ch_range = powers(ch_range); q.ch_logic = powers(ch_logic); q.ch_fixed = powers(ch_fixed); q.ch_var = powers(ch_var);
-    q.edwards_d = to_dev((HFr::from_u64(10240) * HFr::from_u64(10241).inv()).neg());
+    q.edwards_d = P->edwards_d;
     for (int i = 0; i < 8; i++) q.vh_inv[i] = to_dev(P->vh_inv[i]);
     q.has_range = P->has_widget[0]; q.has_logic = P->has_widget[1]; q.has_fixed = P->has_widget[2]; q.has_var = P->has_widget[3];
-    PB_LAUNCH(k_quotient, div_up(n8, 128), 128, 0, st, q);
   }
-  PB_TRY(ntt_run((const uint64_t*)quot, n8, (uint64_t*)tcoef, log_n + 3, 1, 1, 1, n8, n8, st, ar));
-  // quotient_poly.len() > 7n  =>  CircuitUnsatisfied (quotient_poly.rs:132-134); coefficients past
-  // 4n+7 cannot be committed with this key either
-  PB_CUDA(cudaMemsetAsync(flag, 0, 4, st));
-  PB_LAUNCH(k_any_nonzero, div_up(n8 - 7 * n, 256), 256, 0, st, (const uint4*)tcoef, 7 * n, n8, flag);
-  PB_LAUNCH(k_split_quotient, dim3(div_up(stride, 256), 4), 256, 0, st, (const uint4*)tcoef, n, n8, stride, to_dev(BL[11]), to_dev(BL[12]), to_dev(BL[13]), tq);
   unsigned char* stage = (unsigned char*)pinned_scratch(1024, 1);
   if (!stage) return fail(PB200_ERR_CUDA, "pinned staging buffer");
   volatile unsigned& h_flag = *(volatile unsigned*)(stage + 512);
-  PB_CUDA(cudaMemcpyAsync(stage + 512, flag, 4, cudaMemcpyDeviceToHost, st));
+  if (!quot4n) {
+    // coset evaluations of z, a, b, c, d and the public-input polynomial in one batch
+    // (quotient_poly.rs:50-59, 177)
+    PB_TRY(ntt_run((const uint64_t*)zp, n + 3, (uint64_t*)w8, log_n + 3, 0, 1, n_pi ? 6 : 5, stride, n8, st, ar));
+    if (!n_pi) PB_CUDA(cudaMemsetAsync(w8 + 2 * 5 * n8, 0, n8 * 32, st));  // empty PI polynomial: 8n zeros
+    PB_LAUNCH(k_quotient, div_up(n8, 128), 128, 0, st, q);
+    PB_TRY(ntt_run((const uint64_t*)quot, n8, (uint64_t*)tcoef, log_n + 3, 1, 1, 1, n8, n8, st, ar));
+    // quotient_poly.len() > 7n  =>  CircuitUnsatisfied (quotient_poly.rs:132-134); coefficients past
+    // 4n+7 cannot be committed with this key either
+    PB_CUDA(cudaMemsetAsync(flag, 0, 4, st));
+    PB_LAUNCH(k_any_nonzero, div_up(n8 - 7 * n, 256), 256, 0, st, (const uint4*)tcoef, 7 * n, n8, flag);
+    PB_CUDA(cudaMemcpyAsync(stage + 512, flag, 4, cudaMemcpyDeviceToHost, st));
+  } else {
+    // 1. u(X) = t(X) mod (X^4n - g^4n) from the 4n coset
+    PB_TRY(ntt_run((const uint64_t*)zp, n + 3, (uint64_t*)w8, log_n + 2, 0, 1, n_pi ? 6 : 5, stride, n4, st, ar));
+    if (!n_pi) PB_CUDA(cudaMemsetAsync(w8 + 2 * 5 * n4, 0, n4 * 32, st));
+    PB_LAUNCH(k_quotient_4n, div_up(n4, 128), 128, 0, st, q);
+    PB_TRY(ntt_run((const uint64_t*)quot, n4, (uint64_t*)tcoef, log_n + 2, 1, 1, 1, n4, n4, st, ar));
+    // 2. t at the eight points x_k = h w8^k, h = g w_8n (indices 1 + n k of the 8n coset): the witness
+    //    polynomials by Horner at x_k and omega x_k, the prover key from its 8n tables.  The upper half
+    //    of w8 is free in this mode and holds the small arrays.
+    uint4* wpts = w8 + 2 * 6 * n4;   // [6][16]
+    uint4* tx = wpts + 2 * 96;       // t(x_k)
+    uint4* ux = tx + 2 * 8;          // u(x_k)
+    uint4* part4 = ux + 2 * 8;       // partial sums of the evaluations
+    const unsigned blocks4 = div_up(n4, 2048);
+    const Quot4nConsts& qc = P->q4;
+    const int rows = n_pi ? 6 : 5;
+    {
+      EvalRows er;
+      er.base = zp; er.row_stride = stride; er.len = (unsigned)n + 3;
+      for (int j = 0; j < 16; j++) er.point[j] = qc.xs[j];
+      PB_LAUNCH(k_poly_eval_rows, dim3(eval_blocks, 16, rows), 256, 0, st, er, part4, eval_blocks);
+      PB_LAUNCH(k_sum_rows, 16 * rows, 32, 0, st, (const uint4*)part4, eval_blocks, wpts);
+    }
+    if (!n_pi) PB_CUDA(cudaMemsetAsync(wpts + 2 * 16 * 5, 0, 16 * 32, st));
+    QuotArgs qp = q;
+    qp.w8 = wpts;
+    qp.out = tx;
+    PB_LAUNCH(k_quotient_pts, 1, 128, 0, st, qp);
+    {
+      EvalRows er;
+      er.base = tcoef; er.row_stride = 0; er.len = (unsigned)n4;
+      for (int j = 0; j < 16; j++) er.point[j] = qc.xs[j];
+      PB_LAUNCH(k_poly_eval_rows, dim3(blocks4, 8, 1), 256, 0, st, er, part4, blocks4);
+      PB_LAUNCH(k_sum_rows, 8, 32, 0, st, (const uint4*)part4, blocks4, ux);
+    }
+    // 3. t_hi(x_k) = (t(x_k) - u(x_k)) / (x_k^4n - g^4n), and x_k^4n = -g^4n for every k; the 8-point
+    //    inverse DFT on h*H_8 gives its coefficients, the eighth of which must vanish (N divisible by Z_H:
+    //    replaces the reference's len > 7n test, quotient_poly.rs:132-134);  4. t = (u - g^4n t_hi) + X^4n t_hi.
+    //    Both on the device (eight threads), so round 3 has no host synchronisation of its own.
+    PB_CUDA(cudaMemsetAsync(flag, 0, 4, st));
+    PB_LAUNCH(k_quot4n_fix, 1, 32, 0, st, (const uint4*)tx, (const uint4*)ux, tcoef, n4, qc.fix, flag);
+    PB_CUDA(cudaMemcpyAsync(stage + 512, flag, 4, cudaMemcpyDeviceToHost, st));
+    t_len = n4 + 7;
+  }
+  PB_LAUNCH(k_split_quotient, dim3(div_up(stride, 256), 4), 256, 0, st, (const uint4*)tcoef, n, t_len, stride, to_dev(BL[11]), to_dev(BL[12]), to_dev(BL[13]), tq);
   const size_t key_len = srs_len(P->srs);
   const size_t tlen = std::min(stride, key_len);
   PB_TRY(msm_run(P->srs, 0, (const uint64_t*)tq, tlen, 4, stride, aff, st, ar));  // synchronises the stream
@@ -1044,10 +1273,11 @@ int pb200_prove(const pb200_prover_t* p, const uint64_t* witnesses, size_t n_wit
   return rc;
 }
 
-int pb200_prove_dev(const pb200_prover_t* p, const uint64_t* d_witnesses, const uint64_t* pi_idx, const uint64_t* pi_vals,
-                    size_t n_pi, const uint64_t* blinders, uint8_t* out_proof, void* stream) {
+int pb200_prove_dev(const pb200_prover_t* p, const uint64_t* d_witnesses, size_t n_witnesses, const uint64_t* pi_idx,
+                    const uint64_t* pi_vals, size_t n_pi, const uint64_t* blinders, uint8_t* out_proof, void* stream) {
   PB_TRY(ensure_init());
   if (!p || !d_witnesses || !blinders || !out_proof) return fail(PB200_ERR_INVALID_ARG, "null argument");
+  if (n_witnesses != p->n_witnesses) return fail(PB200_ERR_INVALID_ARG, "witness count differs from the compiled circuit");
   cudaStream_t st = stream ? (cudaStream_t)stream : thread_stream();
   return prove_dev(p, d_witnesses, pi_idx, pi_vals, n_pi, blinders, out_proof, st);
 }

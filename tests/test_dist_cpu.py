@@ -69,3 +69,66 @@ def test_host_g1_helpers_match_oracle():
     for p in pts:
         check(lib().pb200_g1_compress(R.g1_to_raw_bytes(p), out))
         assert out.raw == R.g1_compress(p)
+
+
+def test_msm_combine_parts_matches_the_bucket_reduction_formula():
+    """Host tail of the point-sharded MSM (pb200_msm_combine_parts, the finish of pb200_msm_g1_allgather*): the
+    per-digit sums of several ranks are added digit by digit, then R = sum A + g * sum_j 2^shift_j D_j."""
+    import ctypes
+
+    from plonk_b200._lib import check, lib
+
+    rng = random.Random(11)
+    one = ((1 << 384) % R.P_MOD).to_bytes(48, "little")
+
+    def xyzz(p):
+        return bytes(192) if p is None else R.g1_to_raw_bytes(p) + one + one
+
+    for c, n_parts, batch in ((13, 3, 2), (16, 2, 1), (4, 1, 3), (20, 8, 1)):
+        nb = 1 << (c - 1)
+        g = min(8, nb)
+        n_groups = nb // g
+        total_bits = max(0, (n_groups - 1).bit_length())
+        ndig = (total_bits + 3) // 4
+        shifts, sh = [], 0
+        for j in range(ndig):
+            shifts.append(sh)
+            sh += (total_bits - sh) // (ndig - j)
+        wpe = ctypes.c_size_t()
+        check(lib().pb200_msm_combine_parts(None, 0, c, batch, None, ctypes.byref(wpe)))
+        assert wpe.value == (ndig + 1) * 48
+        pts = [[[R.g1_mul(R.G1_GEN, rng.randrange(1, R.R_MOD)) if rng.random() < 0.8 else None for _ in range(ndig + 1)]
+                for _ in range(batch)] for _ in range(n_parts)]
+        blob = b"".join(xyzz(p) for part in pts for entry in part for p in entry)
+        out = ctypes.create_string_buffer(96 * batch)
+        check(lib().pb200_msm_combine_parts(blob, n_parts, c, batch, out, ctypes.byref(wpe)))
+        for b in range(batch):
+            want = None
+            for part in pts:
+                for j in range(ndig):
+                    if part[b][j] is not None:
+                        want = R.g1_add(want, R.g1_mul(part[b][j], g << shifts[j]))
+                want = R.g1_add(want, part[b][ndig])
+            assert R.g1_from_raw_bytes(out.raw[96 * b : 96 * b + 96]) == want, (c, b)
+
+
+def test_sharded_key_slices_and_threshold_logic():
+    """plonk_b200.dist.ShardedCommitKey's host-side bookkeeping (which points a rank reads, when the exchange
+    is skipped) without touching a GPU."""
+    from plonk_b200 import dist as pd
+
+    class FakeComm:
+        def __init__(self, rank, world):
+            self.rank, self.world = rank, world
+
+    k = pd.ShardedCommitKey.__new__(pd.ShardedCommitKey)
+    k.comm, k.n_points, k.threshold = FakeComm(2, 4), 1000, 256
+    k.first, k.count = pd.shard_range(1000, 2, 4)
+    k._replica, k.replica_points = object(), 256
+    assert (k.first, k.count) == (500, 250)
+    assert k.slice_of(1000) == (500, 250) and k.slice_of(600) == (500, 100) and k.slice_of(500) == (500, 0) and k.slice_of(10) == (10, 0)
+    assert not k.uses_collective(256) and k.uses_collective(257)
+    k._replica = None
+    assert k.uses_collective(10)
+    k.comm = FakeComm(0, 1)
+    assert not k.uses_collective(10**6)

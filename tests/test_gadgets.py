@@ -228,3 +228,35 @@ def test_gadget_errors_mirror_the_reference():
     o = G.GadgetComposer.initialized()
     with pytest.raises(ValueError):
         o.component_mul_generator(o.append_witness(G.JUBJUB_ORDER), GEN)
+
+
+def test_witness_only_composer_reproduces_the_witness_table():
+    """The composer of Prover::prove (prover.rs:425) re-runs the circuit for its witnesses only: same witness
+    table, same gate count and public inputs as the full composer, no gate layout kept."""
+    import ctypes
+
+    from plonk_b200._lib import check, lib
+
+    L = lib()
+    full, wo = ctypes.c_void_p(), ctypes.c_void_p()
+    check(L.pb200_composer_new(ctypes.byref(full)))
+    check(L.pb200_composer_new(ctypes.byref(wo)))
+    check(L.pb200_composer_set_witness_only(wo, 1))
+    for h in (full, wo):
+        check(L.pb200_composer_bench_circuit(h, 1 << 12))
+        pub = (5).to_bytes(32, "little")
+        w = ctypes.c_uint32()
+        check(L.pb200_composer_append_public(h, pub, ctypes.byref(w)))
+    n_w, n_g = L.pb200_composer_witnesses(full), L.pb200_composer_constraints(full)
+    assert (L.pb200_composer_witnesses(wo), L.pb200_composer_constraints(wo), L.pb200_composer_public_inputs(wo)) == (n_w, n_g, 1)
+    a, b = ctypes.create_string_buffer(32 * n_w), ctypes.create_string_buffer(32 * n_w)
+    ia, ib = ctypes.create_string_buffer(8), ctypes.create_string_buffer(8)
+    va, vb = ctypes.create_string_buffer(32), ctypes.create_string_buffer(32)
+    check(L.pb200_composer_export(full, None, None, a, ia, va))
+    check(L.pb200_composer_export(wo, None, None, b, ib, vb))
+    assert a.raw == b.raw and ia.raw == ib.raw and va.raw == vb.raw
+    sel = ctypes.create_string_buffer(11 * 32 * n_g)
+    assert L.pb200_composer_export(wo, sel, None, None, None, None) == -4  # no gate layout in this mode
+    assert L.pb200_composer_set_witness_only(wo, 0) == -4
+    L.pb200_composer_free(full)
+    L.pb200_composer_free(wo)

@@ -68,9 +68,6 @@ def test_device_fp_product_forms(pb):
     assert got[2 * n :] == [(x * y - z * w) * rinv % mod for x, y, z, w in zip(a, b, c, d)]
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("PB200_TEST_LAGRANGE"),
-                    reason="pb200_g1_lagrange_key was written after round 1's GPU budget was spent; its algorithm is "
-                           "validated on the host (tests/test_host_arith.py), set PB200_TEST_LAGRANGE=1 to run it on the GPU")
 def test_lagrange_key_matches_direct_sum(pb):
     """Inverse NTT over group elements (csrc/ecntt.cu) against [L_j(x)]G = (1/n) sum_i w^(-ij) [x^i]G, and a
     commitment through evaluations against CommitKey::commit of the interpolated polynomial."""
