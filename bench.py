@@ -274,7 +274,7 @@ def run_ours(args):
     ntt = ntt_microbench(L, torch, imad.value)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(arrays, 1)
+        cpu = cpu_baseline(arrays, 2)
     extra = {}
     if ms_synth is not None:
         host_threads = len(os.sched_getaffinity(0))
@@ -313,8 +313,8 @@ def msm_sweep(L, torch, rank, world, local, args):
     partitioned across the ranks.  Every rank makes its slice of a seeded key [x^i]g on its own GPU, holds the
     full scalar vector in HBM and reads its slice; plonk_b200.dist.ShardedCommitKey runs the slice MSM and the
     device-resident ncclAllGather of the digit sums (pb200_msm_g1_allgather_dev) - or, below its size threshold,
-    the whole MSM on a replicated key with no collective.  The scalars repeat a random 4096-element block, so
-    the result is checked against [g p(x)]G from the closed form p(x) = B(x) * (x^n - 1) / (x^4096 - 1).
+    the whole MSM on a replicated key with no collective.  The scalars are s_i = u[i mod 4096] + v[i div 4096] for
+    random u, v (distinct, full-range), so the result is checked against [g p(x)]G from a closed form.
     Timed with CUDA events on the launching stream, max over ranks, best of `iters`."""
     import random
 
@@ -339,10 +339,13 @@ def msm_sweep(L, torch, rank, world, local, args):
             check(L.pb200_srs_setup_from_secret(mont(x), mont(gs * pow(x, first, R_MOD) % R_MOD), count, slice_raw))
         key = pd.ShardedCommitKey(slice_raw.raw[: 96 * count], n, comm, threshold=threshold, replica_raw=rep_raw.raw[: 96 * min(n, threshold)])
         del slice_raw
-        rng = random.Random(4096 + log_n)  # the same block on every rank
-        block = [rng.randrange(R_MOD) for _ in range(4096)]
-        blk = torch.frombuffer(bytearray(b"".join(mont(v) for v in block)), dtype=torch.int64).view(4096, 4)
-        sc = blk.repeat(n // 4096, 1).contiguous().cuda()
+        # scalars s_i = u[i mod 4096] + v[i div 4096] (mod r) with random u, v: pairwise distinct full-range values
+        # (uniform window digits), and p(x) = U(x) (x^n - 1)/(x^4096 - 1) + V(x^4096) (x^4096 - 1)/(x - 1) in closed form
+        rng = random.Random(4096 + log_n)  # the same on every rank
+        m = 4096
+        u = [rng.randrange(R_MOD) for _ in range(m)]
+        v = [rng.randrange(R_MOD) for _ in range(n // m)]
+        sc = fr_outer_sum(torch, u, v)
         times = []
         total = None
         for it in range(args.msm_iters + 1):
@@ -357,13 +360,19 @@ def msm_sweep(L, torch, rank, world, local, args):
             ms = pd.max_over_ranks(e0.elapsed_time(e1), torch.device("cuda", local))
             if it:
                 times.append(ms)
-        # [g * B(x) * (x^n - 1)/(x^4096 - 1)] G as a one-point "key"
-        bx = 0
-        for v in reversed(block):
-            bx = (bx * x + v) % R_MOD
-        geo = (pow(x, n, R_MOD) - 1) * pow(pow(x, 4096, R_MOD) - 1, -1, R_MOD) % R_MOD
+        # [g p(x)] G as a one-point "key"
+        xm = pow(x, m, R_MOD)
+        ux = 0
+        for c in reversed(u):
+            ux = (ux * x + c) % R_MOD
+        vx = 0
+        for c in reversed(v):
+            vx = (vx * xm + c) % R_MOD
+        geo_n = (pow(x, n, R_MOD) - 1) * pow(xm - 1, -1, R_MOD) % R_MOD
+        geo_m = (xm - 1) * pow(x - 1, -1, R_MOD) % R_MOD
+        px = (ux * geo_n + vx * geo_m) % R_MOD
         want = ctypes.create_string_buffer(96)
-        check(L.pb200_srs_setup_from_secret(mont(1), mont(gs * bx * geo % R_MOD), 1, want))
+        check(L.pb200_srs_setup_from_secret(mont(1), mont(gs * px % R_MOD), 1, want))
         ok = want.raw == total
         best = min(times)
         rows.append({"log_n": log_n, "gpus": world, "ms": best, "points_per_s": n / best * 1e3, "window_bits": key.window,
@@ -377,7 +386,35 @@ def msm_sweep(L, torch, rank, world, local, args):
     if comm is not None:
         comm.destroy()
     return {"sizes": rows, "single_gpu_threshold_points": threshold,
-            "scalars": "random 4096-element block repeated (checkable in closed form; digit statistics of uniform scalars)"}
+            "scalars": "s_i = u[i mod 4096] + v[i div 4096] mod r, u and v uniform: distinct full-range scalars whose polynomial has a closed form"}
+
+
+def fr_outer_sum(torch, u, v):
+    """[len(v) * len(u), 4] int64 tensor on the GPU: Montgomery forms of (u[j] + v[k]) mod r at index k * len(u) + j.
+    Montgomery form is linear, so it is a 256-bit modular addition of the two tables: 32-bit limbs in int64 lanes."""
+    def limbs(vals):
+        raw = b"".join(mont(x) for x in vals)
+        t = torch.frombuffer(bytearray(raw), dtype=torch.int32).view(len(vals), 8).cuda().to(torch.int64)
+        return t & 0xFFFFFFFF
+
+    U, V = limbs(u), limbs(v)
+    r_l = torch.tensor([(R_MOD >> (32 * i)) & 0xFFFFFFFF for i in range(8)], dtype=torch.int64, device="cuda")
+    s = (V[:, None, :] + U[None, :, :]).reshape(-1, 8)  # limb sums < 2^33
+    carry = torch.zeros(s.shape[0], dtype=torch.int64, device="cuda")
+    for i in range(8):
+        t = s[:, i] + carry
+        s[:, i] = t & 0xFFFFFFFF
+        carry = t >> 32
+    # s < 2r < 2^256: subtract r where s >= r
+    d = s.clone()
+    borrow = torch.zeros_like(carry)
+    for i in range(8):
+        t = d[:, i] - r_l[i] - borrow
+        borrow = (t < 0).to(torch.int64)
+        d[:, i] = t & 0xFFFFFFFF
+    ge = (carry > 0) | (borrow == 0)
+    out = torch.where(ge[:, None], d, s)
+    return (out[:, 0::2] | (out[:, 1::2] << 32)).contiguous()
 
 
 def proof_2_20(L, torch):
@@ -458,6 +495,7 @@ def cpu_baseline(arrays, n_proofs):
     srs = cref.srs_from_secret(SRS_POINTS, SRS_X, SRS_G, threads)
     ca = arrays
     prover = cref.CrefProver(LABEL, ca, srs, threads)
+    prover.prove(blinders_for(99), ca)  # warm-up: thread pool, first-touch pages
     t0 = time.time()
     for i in range(n_proofs):
         prover.prove(blinders_for(i), ca)
@@ -478,7 +516,7 @@ def cpu_baseline(arrays, n_proofs):
     msm_s = time.time() - t0
     window = int(math.log(SRS_POINTS)) + 2  # msm_variable_base's window rule
     return {"value": n_proofs / dt, "unit": "proofs/s", "cores": threads, "kind": "port",
-            "sample": f"{n_proofs} proof(s) of the same 2^16-gate circuit, C++/OpenMP restatement of the reference prover "
+            "sample": f"{n_proofs} proof(s) after one warm-up proof of the same 2^16-gate circuit, C++/OpenMP restatement of the reference prover "
                       f"(the Rust crate cannot be built here: no cargo/rustc); "
                       f"{cref.thread_policy()}",
             "coset_ntt_2^19": {"ms": ntt_s * 1e3, "butterflies_per_s": (n19 // 2) * (LOG_GATES + 3) / ntt_s},
@@ -534,7 +572,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--inflight", type=int, default=int(os.environ.get("PB200_INFLIGHT", "8")))
+    ap.add_argument("--inflight", type=int, default=int(os.environ.get("PB200_INFLIGHT", "12")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-msm-sweep", action="store_true", help="skip extra.msm_sweep (BASELINE.json configs[3])")
     ap.add_argument("--msm-sizes", default="16,18,20,22,24", help="log2 point counts of the sharded-MSM sweep")

@@ -72,41 +72,31 @@ def _cgroup_cpu_limit() -> Optional[int]:
 _best_threads: Optional[int] = None
 
 
-def _physical_cores() -> int:
-    """Distinct physical cores among the CPUs this process may run on (SMT siblings counted once)."""
-    try:
-        cpus = sorted(os.sched_getaffinity(0))
-    except AttributeError:
-        return os.cpu_count() or 1
-    cores = set()
-    for c in cpus:
-        try:
-            sib = open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list").read().strip()
-        except OSError:
-            sib = str(c)
-        cores.add(sib)
-    return max(1, len(cores))
+PORT_MAX_THREADS = 32
 
 
 def best_threads() -> int:
     """Thread count of the CPU baseline - ONE fixed policy, so that the number does not swing with a
-    calibration run: every physical core this process may run on (SMT siblings once), capped by the
-    container's CPU quota; PB200_CPU_THREADS overrides.  (Round 1 picked the fastest of T, T/2, T/4 on a
-    short sample, which chose 16, 48 or 96 threads on different boxes.)"""
+    calibration run (round 1 picked the fastest of T, T/2, T/4 on a short sample, which chose 16, 48 or 96
+    threads on different boxes): min(32, the CPUs this process may run on, the container's CPU quota).
+    32 is where the restatement stops scaling - its MSM is window-parallel (20 windows at 2^16 points) and
+    the prover runs 4- to 5-way outer concurrency like the reference's rayon::join sites - and more threads
+    were measured slower (0.27 proofs/s at 64 threads against 0.66 at 16 on a 128-CPU box).
+    PB200_CPU_THREADS overrides."""
     global _best_threads
     if _best_threads is None:
         if os.environ.get("PB200_CPU_THREADS"):
             _best_threads = threads()
         else:
-            top = _physical_cores()
+            top = min(PORT_MAX_THREADS, threads())
             limit = _cgroup_cpu_limit()
             _best_threads = max(1, min(top, limit) if limit else top)
     return _best_threads
 
 
 def thread_policy() -> str:
-    return (f"{best_threads()} threads = every physical core usable by this process ({threads()} logical CPUs), capped by the "
-            "cgroup CPU quota; fixed policy, PB200_CPU_THREADS overrides")
+    return (f"{best_threads()} threads = min({PORT_MAX_THREADS}, the {threads()} CPUs usable by this process, the cgroup CPU quota): "
+            "fixed policy (the restatement stops scaling there), PB200_CPU_THREADS overrides")
 
 
 def _default_threads(work_items: int) -> int:

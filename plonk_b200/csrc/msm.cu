@@ -39,11 +39,13 @@ namespace pb {
 
 static constexpr int kGroup = 8;
 static constexpr unsigned kClassChunk = 512;  // members of a class summed by one warp
-// Buckets longer than kHeavy size units (the unit is chosen so that the average bucket of a dense MSM is
-// 32..64 units, i.e. > 2.5x .. 5x the average) leave the one-thread-group-per-bucket kernel: they are cut
-// into chunks of kHeavyChunk entries, one warp per chunk, and the chunk sums are added per bucket afterwards.
-// A lane of k_msm_accumulate therefore never walks more than kHeavy << size_shift >> log_split entries.
-static constexpr unsigned kHeavy = 160;
+// Over-long buckets leave the one-thread-group-per-bucket kernel: they are cut into chunks of kHeavyChunk
+// entries, one warp per chunk, and the chunk sums are added per bucket afterwards.  "Over-long" is decided
+// on the device from the MSM's actual load (k_msm_scan): more than max(kHeavyMin, kHeavyFactor x the average
+// bucket) entries.  A dense MSM (uniform scalars, average 32..64) never has such a bucket; a sparse one (the
+// wire VALUES of a circuit: average 2, a tail of buckets with dozens to tens of thousands of entries) sends
+// its tail there, so that no lane of k_msm_accumulate walks more than a few dozen entries.
+static constexpr unsigned kHeavyMin = 32, kHeavyFactor = 4;
 static constexpr unsigned kHeavyChunk = 256;
 
 PB_D G1Affine ld_affine(const uint4* p, size_t i) {
@@ -264,21 +266,26 @@ __global__ void k_msm_digits(const uint4* scalars, size_t n, size_t stride, int 
 // clipped size), so that the threads of a warp in k_msm_accumulate get buckets of near-equal length
 // and the warp does not idle on its longest lane.
 __global__ void __launch_bounds__(1024) k_msm_scan(const unsigned* counts, unsigned* offsets, unsigned* order, unsigned* n_heavy,
-                                                   unsigned* heavy_pre, unsigned nb, int size_shift) {
+                                                   unsigned* heavy_pre, unsigned* max_len, unsigned nb, int size_shift) {
   __shared__ unsigned sums[1024];
   __shared__ unsigned bins[1024];
-  __shared__ unsigned s_nh;
+  __shared__ unsigned s_nh, s_total, s_thr_units, s_max;
   const unsigned b = blockIdx.x, tid = threadIdx.x;
   const unsigned* cnt = counts + (size_t)b * nb;
   unsigned* off = offsets + (size_t)b * (nb + 1);
   unsigned* ord = order + (size_t)b * nb;
   const unsigned chunk = (nb + 1023) / 1024;
   const unsigned lo = tid * chunk, hi = min(nb, lo + chunk);
-  unsigned s = 0;
-  for (unsigned k = lo; k < hi; k++) s += cnt[k];
+  unsigned s = 0, mx = 0;
+  for (unsigned k = lo; k < hi; k++) {
+    s += cnt[k];
+    mx = max(mx, cnt[k]);
+  }
   sums[tid] = s;
   bins[tid] = 0;
+  if (tid == 0) s_max = 0;
   __syncthreads();
+  if (mx) atomicMax(&s_max, mx);
   for (unsigned d = 1; d < 1024; d <<= 1) {
     unsigned v = (tid >= d) ? sums[tid - d] : 0;
     __syncthreads();
@@ -290,7 +297,11 @@ __global__ void __launch_bounds__(1024) k_msm_scan(const unsigned* counts, unsig
     off[k] = run;
     run += cnt[k];
   }
-  if (tid == 1023) off[nb] = sums[1023];
+  if (tid == 1023) {
+    off[nb] = sums[1023];
+    s_total = sums[1023];
+    max_len[b] = s_max;  // the scan loops above passed several barriers since the atomicMax
+  }
   // counting sort of the buckets by size (in units of 2^size_shift entries, so that the average
   // bucket lands near bin 64 whatever the MSM size), largest first (bin 0 = size >= 1023 units)
   for (unsigned k = tid; k < nb; k += 1024) atomicAdd(&bins[1023u - min(cnt[k] >> size_shift, 1023u)], 1u);
@@ -306,7 +317,14 @@ __global__ void __launch_bounds__(1024) k_msm_scan(const unsigned* counts, unsig
   }
   bins[tid] = sums[tid] - mine;  // exclusive start of each bin
   // buckets are ordered largest first, so the heavy ones are order[0 .. n_heavy)
-  if (tid == 1022u - kHeavy) {  // bins 0 .. 1022-kHeavy hold the sizes > kHeavy
+  // heavy: more than thr_units size units, thr = max(kHeavyMin, kHeavyFactor * average) entries rounded up to units
+  if (tid == 0) {
+    const unsigned avg = s_total / nb;
+    const unsigned thr = max(kHeavyMin, kHeavyFactor * avg);
+    s_thr_units = min(1021u, (thr + (1u << size_shift) - 1u) >> size_shift);
+  }
+  __syncthreads();
+  if (tid == 1022u - s_thr_units) {  // bins 0 .. 1022-thr hold the sizes > thr units
     n_heavy[b] = sums[tid];
     s_nh = sums[tid];
   }
@@ -480,6 +498,295 @@ __global__ void __launch_bounds__(128) k_msm_heavy_combine(const uint4* partials
 }
 
 // ---------------------------------------------------------------------------------------------
+// Bucket accumulation by batched affine additions (the default since round 2; PB200_MSM_AFFINE=0 selects
+// the XYZZ kernels above).
+//
+// An affine addition needs lambda = (y2 - y1) / (x2 - x1): 2M + 1S once 1 / (x2 - x1) is known, against
+// 8M + 2S for the inversion-free XYZZ mixed addition.  Inversions are shared with Montgomery's trick
+// (3M per element), which needs MANY INDEPENDENT additions at a time - a serial walk along a bucket has
+// none.  So the entries of every bucket are added as a tree: in round r the surviving elements
+// (2i, 2i + 1) of each bucket are added pairwise, all pairs of all buckets being independent; a bucket of L
+// entries is done after ceil(log2 L) rounds, and the total number of additions is unchanged (L - 1).
+//   * Layout.  Round 0 reads table points through the sorted (point, sign) references, bucket b at
+//     [off[b], off[b] + L).  The output of round r is layout r + 1: bucket b keeps ceil(L_r / 2) elements at
+//     off_{r+1}[b] = (off_r[b] + b) >> 1, which never overlaps its neighbour and shrinks the buffers by half
+//     per round (two ping-pong buffers of cap/2 + nb and cap/4 + nb points).  A bucket's last addition
+//     writes sums[b]; single-entry buckets are copied there by round 0; sums is pre-zeroed (identity).
+//   * Work split.  A thread owns kAffK consecutive input POSITIONS of the round's layout, whatever buckets
+//     they belong to (binary search for the first one), i.e. up to kAffK/2 pairs: a 30 000-entry bucket and
+//     30 000 single-pair buckets are the same work list.  No bucket ordering, no heavy-bucket path.
+//   * Inversions.  Phase A: the thread walks its pairs, d_i = x2 - x1 (2 y1 for a doubling, 1 when a pair
+//     needs no division: an identity operand or P + (-P)), stores the running product before d_i in
+//     scratch.  Phase B: the CTA's 128 thread totals are inverted together - warp prefix/suffix products by
+//     shuffles, ONE inversion per CTA by lane 0 with a binary extended GCD on the integer-add pipe (the
+//     multiply pipe is the bottleneck of these kernels and stays free for the other warps and CTAs).
+//     Phase C: the thread walks back, 1/d_i = (running inverse) x (stored prefix), and finishes each
+//     addition: 5M + 1S + ~0.4M of sharing per addition, 32 % fewer multiply instructions than XYZZ.
+// ---------------------------------------------------------------------------------------------
+static constexpr int kAffK = 64;         // input positions per thread
+static constexpr int kAffThreads = 128;  // 4096 pairs share one inversion
+
+PB_D unsigned aff_off(unsigned o, unsigned b, int r) {
+  for (int i = 0; i < r; i++) o = (o + b) >> 1;
+  return o;
+}
+PB_D unsigned aff_len(unsigned L, int r) { return (L + (1u << r) - 1u) >> r; }
+
+PB_D Fp shfl_fp(const Fp& a, int src_lane) {
+  Fp r;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r.v[i] = __shfl_sync(0xffffffffu, a.v[i], src_lane);
+  return r;
+}
+PB_D Fp shfl_up_fp(const Fp& a, int d) {
+  Fp r;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r.v[i] = __shfl_up_sync(0xffffffffu, a.v[i], d);
+  return r;
+}
+PB_D Fp shfl_down_fp(const Fp& a, int d) {
+  Fp r;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r.v[i] = __shfl_down_sync(0xffffffffu, a.v[i], d);
+  return r;
+}
+
+// (aR)^-1 R for a Montgomery residue aR != 0, by the binary extended Euclidean algorithm (shifts, adds and
+// subtractions only; data-dependent control flow, meant for ONE lane).  0 -> 0.
+__device__ __noinline__ Fp fp_inv_bingcd(Fp a) {
+  if (a.is_zero()) return a;
+  uint32_t u[12], v[12], x1[12], x2[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    u[i] = a.v[i];
+    v[i] = FpParams::MOD(i);
+    x1[i] = i == 0 ? 1u : 0u;
+    x2[i] = 0u;
+  }
+  auto is_one = [](const uint32_t* t) {
+    uint32_t x = t[0] ^ 1u;
+#pragma unroll
+    for (int i = 1; i < 12; i++) x |= t[i];
+    return x == 0;
+  };
+  auto halve = [](uint32_t* t, uint32_t* x) {  // t even: t /= 2, x = x / 2 mod p
+#pragma unroll
+    for (int i = 0; i < 11; i++) t[i] = __funnelshift_r(t[i], t[i + 1], 1);
+    t[11] >>= 1;
+    const uint32_t m = 0u - (x[0] & 1u);  // odd: add p first (x + p < 2^382)
+    x[0] = add_cc(x[0], FpParams::MOD(0) & m);
+#pragma unroll
+    for (int i = 1; i < 11; i++) x[i] = addc_cc(x[i], FpParams::MOD(i) & m);
+    x[11] = addc(x[11], FpParams::MOD(11) & m);
+#pragma unroll
+    for (int i = 0; i < 11; i++) x[i] = __funnelshift_r(x[i], x[i + 1], 1);
+    x[11] >>= 1;
+  };
+  auto sub_mod = [](uint32_t* x, const uint32_t* y) {  // x = x - y mod p
+    x[0] = sub_cc(x[0], y[0]);
+#pragma unroll
+    for (int i = 1; i < 12; i++) x[i] = subc_cc(x[i], y[i]);
+    const uint32_t m = subc(0u, 0u);  // all ones on borrow
+    x[0] = add_cc(x[0], FpParams::MOD(0) & m);
+#pragma unroll
+    for (int i = 1; i < 11; i++) x[i] = addc_cc(x[i], FpParams::MOD(i) & m);
+    x[11] = addc(x[11], FpParams::MOD(11) & m);
+  };
+#pragma unroll 1
+  while (!is_one(u) && !is_one(v)) {
+#pragma unroll 1
+    while (!(u[0] & 1u)) halve(u, x1);
+#pragma unroll 1
+    while (!(v[0] & 1u)) halve(v, x2);
+    uint32_t t[12];
+    t[0] = sub_cc(u[0], v[0]);
+#pragma unroll
+    for (int i = 1; i < 12; i++) t[i] = subc_cc(u[i], v[i]);
+    const uint32_t borrow = subc(0u, 0u);
+    if (borrow == 0u) {  // u >= v
+#pragma unroll
+      for (int i = 0; i < 12; i++) u[i] = t[i];
+      sub_mod(x1, x2);
+    } else {
+      v[0] = sub_cc(v[0], u[0]);
+#pragma unroll
+      for (int i = 1; i < 12; i++) v[i] = subc_cc(v[i], u[i]);
+      sub_mod(x2, x1);
+    }
+  }
+  Fp y;
+  const bool from_u = is_one(u);
+#pragma unroll
+  for (int i = 0; i < 12; i++) y.v[i] = from_u ? x1[i] : x2[i];
+  return (y * Fp::r2()) * Fp::r2();  // (aR)^-1 -> (aR)^-1 R^2 = a^-1 R
+}
+
+// What one pair needs: the divisor and, later, the numerator of lambda.
+//   kind 0: generic addition (d = x2 - x1, num = y2 - y1);  1: doubling (d = 2 y1, num = 3 x1^2);
+//   2: result = P1 (P2 is the identity);  3: result = P2;  4: result = identity (P2 = -P1)
+PB_D int aff_classify(const G1Affine& p1, const G1Affine& p2, Fp* d) {
+  if (p2.is_inf()) return 2;
+  if (p1.is_inf()) return 3;
+  const Fp dx = p2.x - p1.x;
+  if (!dx.is_zero()) {
+    *d = dx;
+    return 0;
+  }
+  if (p1.y == p2.y && !p1.y.is_zero()) {
+    *d = p1.y.dbl();
+    return 1;
+  }
+  return 4;
+}
+PB_D G1Affine aff_finish(int kind, const G1Affine& p1, const G1Affine& p2, const Fp& inv_d) {
+  if (kind == 2) return p1;
+  if (kind == 3) return p2;
+  G1Affine r;
+  if (kind == 4) {
+    r.x = Fp::zero();
+    r.y = Fp::zero();
+    return r;
+  }
+  Fp num;
+  if (kind == 0) {
+    num = p2.y - p1.y;
+  } else {
+    const Fp xx = p1.x.sqr();
+    num = xx.dbl() + xx;
+  }
+  const Fp lam = num * inv_d;
+  r.x = lam.sqr() - p1.x - p2.x;
+  r.y = lam * (p1.x - r.x) - p1.y;
+  return r;
+}
+
+struct AffRound {
+  const uint4* table;      // commit-key table (round 0 operands)
+  const unsigned* sorted;  // [batch][cap] (point, sign) references in bucket order (round 0)
+  const uint4* in;         // [batch][in_cap] points of layout r (r > 0)
+  uint4* out;              // [batch][out_cap] layout r + 1
+  const unsigned* offsets; // [batch][nb + 1]
+  const unsigned* max_len; // [batch] longest bucket
+  uint4* prefix;           // [batch][pair slots] running products (48 B each)
+  uint2* desc;             // [batch][pair slots] (first input position, output slot)
+  uint4* sums;             // [batch][nb] affine bucket sums
+  unsigned nb;
+  size_t cap, in_cap, out_cap, slots;  // slots = threads per batch entry * kAffK / 2
+  unsigned threads;                    // threads per batch entry in this round
+  int r;
+};
+
+template <bool FIRST>
+PB_D G1Affine aff_load(const AffRound& a, unsigned b, unsigned pos) {
+  if (FIRST) {
+    const unsigned e = __ldg(a.sorted + (size_t)b * a.cap + pos);
+    G1Affine p = ld_affine(a.table, e >> 1);
+    if ((e & 1u) && !p.is_inf()) p.y = p.y.neg();
+    return p;
+  } else {
+    const uint4* q = a.in + 6 * ((size_t)b * a.in_cap + pos);
+    G1Affine p;
+    p.x = ld_fp(q);
+    p.y = ld_fp(q + 3);
+    return p;
+  }
+}
+PB_D void aff_store(const AffRound& a, unsigned b, unsigned slot, const G1Affine& p) {
+  if (slot & 0x80000000u)
+    st_affine(a.sums, (size_t)b * a.nb + (slot & 0x7fffffffu), p);
+  else
+    st_affine(a.out, (size_t)b * a.out_cap + slot, p);
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(kAffThreads) k_msm_affine_round(AffRound a) {
+  __shared__ uint4 sh_tot[4][3];
+  __shared__ uint4 sh_inv[4][3];
+  const unsigned b = blockIdx.y;
+  const int r = a.r;
+  if (r > 0 && (1u << r) >= a.max_len[b]) return;  // every bucket is finished (uniform per CTA)
+  const unsigned* off = a.offsets + (size_t)b * (a.nb + 1);
+  const unsigned nb = a.nb;
+  const unsigned t = blockIdx.x * kAffThreads + threadIdx.x;
+  const unsigned total = aff_off(off[nb], nb, r);  // end of layout r
+  const unsigned pos0 = t * kAffK, pos1 = min(total, pos0 + kAffK);
+  const size_t slot0 = (size_t)b * a.slots + t;  // pair i of this thread lives at slot0 + i * threads
+  Fp run = Fp::one();
+  int np = 0;
+  if (pos0 < total) {
+    // first bucket whose range reaches past pos0: the largest bk with off_r[bk] <= pos0
+    unsigned lo = 0, hi = nb;  // off_r[0] = 0 <= pos0
+    while (hi - lo > 1) {
+      const unsigned mid = (lo + hi) >> 1;
+      if (aff_off(off[mid], mid, r) <= pos0) lo = mid; else hi = mid;
+    }
+    for (unsigned bk = lo; bk < nb; bk++) {
+      const unsigned o = aff_off(off[bk], bk, r);
+      if (o >= pos1) break;
+      const unsigned L0 = off[bk + 1] - off[bk];
+      const unsigned L = aff_len(L0, r);
+      if (L == 0) continue;
+      if (L == 1) {
+        if (FIRST && o >= pos0) aff_store(a, b, 0x80000000u | bk, aff_load<FIRST>(a, b, o));  // single entry: the bucket sum
+        continue;
+      }
+      const unsigned o_next = aff_off(off[bk], bk, r + 1);
+      unsigned e = o >= pos0 ? 0u : ((pos0 - o + 1u) & ~1u);  // first even element at or after pos0
+      for (; e + 1 < L && o + e < pos1; e += 2) {
+        const G1Affine p1 = aff_load<FIRST>(a, b, o + e), p2 = aff_load<FIRST>(a, b, o + e + 1);
+        Fp d = Fp::one();
+        aff_classify(p1, p2, &d);
+        const size_t s = slot0 + (size_t)np * a.threads;
+        st_fp(a.prefix + 3 * s, run);
+        a.desc[s] = make_uint2(o + e, L == 2 ? (0x80000000u | bk) : (o_next + (e >> 1)));
+        run = run * d;
+        np++;
+      }
+      if ((L & 1u) && o + L - 1 >= pos0 && o + L - 1 < pos1)  // odd element out: moves on unchanged
+        aff_store(a, b, o_next + ((L - 1) >> 1), aff_load<FIRST>(a, b, o + L - 1));
+    }
+  }
+  // ---- phase B: invert the 128 thread totals together ----
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Fp incl = run, sfx = run;
+#pragma unroll 1
+  for (int d = 1; d < 32; d <<= 1) {
+    const Fp up = shfl_up_fp(incl, d), dn = shfl_down_fp(sfx, d);
+    if (lane >= d) incl = incl * up;
+    if (lane + d < 32) sfx = sfx * dn;
+  }
+  Fp before = shfl_up_fp(incl, 1), after = shfl_down_fp(sfx, 1);  // products of the lanes below / above
+  if (lane == 0) before = Fp::one();
+  if (lane == 31) after = Fp::one();
+  if (lane == 31) st_fp(sh_tot[warp], incl);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const Fp w0 = ld_fp(sh_tot[0]), w1 = ld_fp(sh_tot[1]), w2 = ld_fp(sh_tot[2]), w3 = ld_fp(sh_tot[3]);
+    const Fp w01 = w0 * w1, w23 = w2 * w3;
+    const Fp inv = fp_inv_bingcd(w01 * w23);
+    const Fp i01 = inv * w23, i23 = inv * w01;  // 1/(w0 w1), 1/(w2 w3)
+    st_fp(sh_inv[0], i01 * w1);
+    st_fp(sh_inv[1], i01 * w0);
+    st_fp(sh_inv[2], i23 * w3);
+    st_fp(sh_inv[3], i23 * w2);
+  }
+  __syncthreads();
+  Fp inv_run = ld_fp(sh_inv[warp]) * (before * after);  // 1 / (this thread's product)
+  // ---- phase C: walk back, finish the additions ----
+#pragma unroll 1
+  for (int i = np - 1; i >= 0; i--) {
+    const size_t s = slot0 + (size_t)i * a.threads;
+    const uint2 ds = a.desc[s];
+    const G1Affine p1 = aff_load<FIRST>(a, b, ds.x), p2 = aff_load<FIRST>(a, b, ds.x + 1);
+    Fp d = Fp::one();
+    const int kind = aff_classify(p1, p2, &d);
+    const Fp inv_d = inv_run * ld_fp(a.prefix + 3 * s);
+    inv_run = inv_run * d;
+    aff_store(a, b, ds.y, aff_finish(kind, p1, p2, inv_d));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Bucket reduction  R = sum_b (b + 1) B_b.  A single GPU thread needs ~15 us per dependent group
 // addition (14 carry-chained Fp products), so the reduction is organised to be work-efficient first
 // (it shares the SMs with other proofs' accumulation kernels) and shallow second:
@@ -502,6 +809,7 @@ struct DigitPlan {
   int nclasses;
 };
 
+template <bool AFFINE>
 __global__ void __launch_bounds__(64) k_msm_groups(const uint4* sums, unsigned nb, int g, uint4* S, uint4* A) {
   const unsigned G = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned n_groups = nb / g;
@@ -509,8 +817,13 @@ __global__ void __launch_bounds__(64) k_msm_groups(const uint4* sums, unsigned n
   const unsigned b = blockIdx.y;
   G1Xyzz run = G1Xyzz::identity(), acc = G1Xyzz::identity();
   for (int j = g - 1; j >= 0; j--) {
-    G1Xyzz q = ld_xyzz(sums, (size_t)b * nb + (size_t)G * g + j);
-    xyzz_add(run, q);
+    if (AFFINE) {  // bucket sums left by the batched-affine rounds: a mixed addition
+      const G1Affine q = ld_affine(sums, (size_t)b * nb + (size_t)G * g + j);
+      if (!q.is_inf()) xyzz_madd(run, q.x, q.y);
+    } else {
+      G1Xyzz q = ld_xyzz(sums, (size_t)b * nb + (size_t)G * g + j);
+      xyzz_add(run, q);
+    }
     xyzz_add(acc, run);
   }
   st_xyzz(S, (size_t)b * n_groups + G, run);
@@ -753,7 +1066,12 @@ static int msm_enqueue(const pb200_srs* srs, size_t first, const uint64_t* d_sca
   PB_ALLOC(scope, counts, (size_t)batch * nb * 4);
   PB_ALLOC(scope, offsets, (size_t)batch * (nb + 1) * 4);
   PB_ALLOC(scope, order, (size_t)batch * nb * 4);
-  unsigned *n_heavy = nullptr, *heavy_pre = nullptr;
+  static const bool affine = [] {
+    const char* e = getenv("PB200_MSM_AFFINE");
+    return e && atoi(e) != 0;
+  }();
+  unsigned *n_heavy = nullptr, *heavy_pre = nullptr, *max_len = nullptr;
+  PB_ALLOC(scope, max_len, (size_t)batch * 4);
   PB_ALLOC(scope, n_heavy, (size_t)batch * 4);
   PB_ALLOC(scope, heavy_pre, (size_t)batch * (nb + 1) * 4);
   PB_ALLOC(scope, ebkt, (size_t)batch * cap * 4);
@@ -772,13 +1090,48 @@ static int msm_enqueue(const pb200_srs* srs, size_t first, const uint64_t* d_sca
   int size_shift = 0;  // size unit: average bucket ~ 64 units
   while (((cap / nb) >> size_shift) > 64) size_shift++;
   // chunk sums of the heavy buckets: at most cap / kHeavyChunk full chunks plus one ragged chunk per heavy bucket
-  const size_t part_cap = cap / kHeavyChunk + cap / ((size_t)kHeavy << size_shift) + 2;
+  const size_t part_cap = cap / kHeavyChunk + std::min<size_t>(nb, cap / kHeavyMin) + 2;
   uint4* partials = nullptr;
   PB_ALLOC(scope, partials, (size_t)batch * part_cap * 192);
-  PB_LAUNCH(k_msm_scan, batch, 1024, 0, st, counts, offsets, order, n_heavy, heavy_pre, nb, size_shift);
+  PB_LAUNCH(k_msm_scan, batch, 1024, 0, st, counts, offsets, order, n_heavy, heavy_pre, max_len, nb, size_shift);
   PB_LAUNCH(k_msm_scatter, dim3(div_up(n, 256), W, batch), 256, 0, st, ebkt, epos, offsets, n, W, nb,
             srs->n_points, first, sorted);
   if (prof_ev) PB_CUDA(cudaEventRecord(prof_ev[0], st));
+  if (affine) {
+    // batched-affine pairwise rounds (see k_msm_affine_round)
+    const size_t capA = cap / 2 + nb + 2, capB = cap / 4 + nb + 2;
+    const unsigned threads0 = div_up(div_up(cap, kAffK), kAffThreads) * kAffThreads;
+    const size_t slots = (size_t)threads0 * (kAffK / 2);
+    uint4 *bufA = nullptr, *bufB = nullptr, *pre = nullptr;
+    uint2* desc = nullptr;
+    PB_ALLOC(scope, bufA, (size_t)batch * capA * 96);
+    PB_ALLOC(scope, bufB, (size_t)batch * capB * 96);
+    PB_ALLOC(scope, pre, (size_t)batch * slots * 48);
+    PB_ALLOC(scope, desc, (size_t)batch * slots * 8);
+    PB_CUDA(cudaMemsetAsync(sums, 0, (size_t)batch * nb * 96, st));
+    int rounds = 0;
+    while (((size_t)1 << rounds) < cap) rounds++;  // a bucket can hold every entry (equal scalars with equal digits)
+    for (int r = 0; r < rounds; r++) {
+      AffRound a;
+      a.table = srs->table; a.sorted = sorted; a.offsets = offsets; a.max_len = max_len; a.prefix = pre; a.desc = desc; a.sums = sums;
+      a.nb = nb; a.cap = cap; a.r = r;
+      a.in = (r & 1) ? bufA : bufB;   // layout r: odd layouts live in A, even ones (>= 2) in B
+      a.out = (r & 1) ? bufB : bufA;  // layout r + 1
+      a.in_cap = (r & 1) ? capA : capB;
+      a.out_cap = (r & 1) ? capB : capA;
+      const size_t positions = (cap >> r) + nb + 1;
+      const unsigned ctas = div_up(div_up(positions, kAffK), kAffThreads);
+      a.threads = ctas * kAffThreads;
+      a.slots = slots;
+      if (r == 0)
+        PB_LAUNCH(k_msm_affine_round<true>, dim3(ctas, batch), kAffThreads, 0, st, a);
+      else
+        PB_LAUNCH(k_msm_affine_round<false>, dim3(ctas, batch), kAffThreads, 0, st, a);
+    }
+    if (prof_ev) PB_CUDA(cudaEventRecord(prof_ev[1], st));
+    if (d_totals) *d_totals = offsets + nb;
+    PB_LAUNCH(k_msm_groups<true>, dim3(div_up(n_groups, 64), batch), 64, 0, st, (const uint4*)sums, nb, g, S, A);
+  } else {
   {
     // CTA shape: 64 threads x 4 CTAs/SM and 128 x 2 hold the same 8 warps per SM (register-limited);
     // the smaller CTA balances the tail of the launch better when there are few waves.  Forcing 12 or
@@ -800,7 +1153,8 @@ static int msm_enqueue(const pb200_srs* srs, size_t first, const uint64_t* d_sca
   PB_LAUNCH(k_msm_heavy_chunks, dim3(592, batch), 128, 0, st, srs->table, sorted, offsets, order, n_heavy, heavy_pre, nb, cap, part_cap, partials);
   PB_LAUNCH(k_msm_heavy_combine, dim3(64, batch), 128, 0, st, (const uint4*)partials, order, n_heavy, heavy_pre, nb, part_cap, sums);
   if (prof_ev) PB_CUDA(cudaEventRecord(prof_ev[1], st));  // the bucket-accumulation phase: every entry has been added once
-  PB_LAUNCH(k_msm_groups, dim3(div_up(n_groups, 64), batch), 64, 0, st, (const uint4*)sums, nb, g, S, A);
+    PB_LAUNCH(k_msm_groups<false>, dim3(div_up(n_groups, 64), batch), 64, 0, st, (const uint4*)sums, nb, g, S, A);
+  }
   PB_LAUNCH(k_msm_group_classes, dim3(div_up(plan.nclasses, 4), batch, chunks), 128, 0, st, (const uint4*)S, (const uint4*)A,
             n_groups, plan, chunks, classes);
   PB_LAUNCH(k_msm_final, batch, 256, 0, st, (const uint4*)classes, plan, chunks, result);
@@ -1006,7 +1360,7 @@ size_t msm_workspace_bytes(const pb200_srs* srs, size_t n, uint32_t batch) {
   {
     int size_shift = 0;
     while (((cap / nb) >> size_shift) > 64) size_shift++;
-    b += (size_t)batch * (cap / kHeavyChunk + cap / ((size_t)kHeavy << size_shift) + 2) * 192 + 256;  // partials
+    b += (size_t)batch * (cap / kHeavyChunk + std::min<size_t>(nb, cap / kHeavyMin) + 2) * 192 + 256;  // partials
   }
   b += (size_t)batch * 4 + 256;                        // n_heavy
   b += 3 * ((size_t)batch * cap * 4 + 256);            // ebkt, epos, sorted
@@ -1014,6 +1368,11 @@ size_t msm_workspace_bytes(const pb200_srs* srs, size_t n, uint32_t batch) {
   b += 2 * ((size_t)batch * n_groups * 192 + 256);     // S, A
   b += (size_t)batch * (8 * 16 + n_groups / 256 + 2) * (n_groups / (16 * kClassChunk) + 2) * 192 + 256;  // classes x chunks
   b += (size_t)batch * 9 * 192 + 256;                  // result
+  {  // batched-affine rounds: two point buffers, running products, pair descriptors
+    const size_t threads0 = ((cap + kAffK - 1) / kAffK + kAffThreads - 1) / kAffThreads * kAffThreads;
+    b += (size_t)batch * ((cap / 2 + nb + 2) + (cap / 4 + nb + 2)) * 96 + 512;
+    b += (size_t)batch * threads0 * (kAffK / 2) * (48 + 8) + 512;
+  }
   return b + 4096;
 }
 
@@ -1050,12 +1409,12 @@ int srs_upload(const uint8_t* raw, size_t n_points, pb200_srs** out) { return sr
 const uint4* srs_points(const pb200_srs* s) { return s->table; }
 
 // srs_upload for points that are already on the device (e.g. the Lagrange form made by csrc/ecntt.cu).
-int srs_from_device(const uint4* d_points, size_t n_points, pb200_srs** out) {
+int srs_from_device(const uint4* d_points, size_t n_points, pb200_srs** out, int window_bits) {
   if (n_points == 0) return fail(PB200_ERR_INVALID_ARG, "empty commit key");
   cudaStream_t st = thread_stream();
   pb200_srs* s = new pb200_srs();
   s->n_points = n_points;
-  s->c = pick_window(n_points);
+  s->c = window_bits ? window_bits : pick_window(n_points);
   s->W = (256 + s->c - 1) / s->c;
   s->table = nullptr;
   cudaError_t e = cudaMalloc((void**)&s->table, (size_t)s->W * n_points * 96);

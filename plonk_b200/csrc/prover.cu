@@ -38,7 +38,8 @@ int srs_upload(const uint8_t* raw, size_t n_points, pb200_srs** out);
 void srs_free(pb200_srs* s);
 size_t srs_len(const pb200_srs* s);
 const uint4* srs_points(const pb200_srs* s);
-int srs_from_device(const uint4* d_points, size_t n_points, pb200_srs** out);
+int srs_from_device(const uint4* d_points, size_t n_points, pb200_srs** out, int window_bits);
+int msm_window_for(size_t n_points);
 int lagrange_key_dev(const uint4* d_in, int log_n, uint4* d_out, cudaStream_t st);
 int get_twiddles(int logm, bool inverse, cudaStream_t st, const uint4** out);
 int fill_powers(uint4* out, size_t n, const Fr& base, const Fr& scale, cudaStream_t st);
@@ -427,7 +428,39 @@ __global__ void k_split_quotient(const uint4* t, size_t n, size_t n8, size_t str
   stg_fr(out, (size_t)k * stride + i, v);
 }
 
-// Polynomial::evaluate for a batch of (poly, point) jobs: chunked Horner + CTA tree sum.
+// Polynomial::evaluate (polynomial.rs:120-137) for batches of (polynomial, point) jobs.  A CTA evaluates a
+// block of 2048 coefficients: P_blk(x) = sum_{i < 2048} c[2048 blk + i] x^i - every thread runs Horner over
+// its 8 coefficients, then a shared-memory tree folds the 256 thread values with the powers x^8, x^16, ...
+// (about 27 products per thread; the first version raised x to each thread's offset with a 64-bit
+// exponent, ~90 products).  k_sum_rows then runs Horner over the blocks with x^2048.
+PB_D void cta_poly_eval(const uint4* poly, unsigned len, const Fr& x, uint4* out_slot) {
+  __shared__ uint4 sh[256][2];
+  const int tid = threadIdx.x;
+  const size_t base = ((size_t)blockIdx.x * 256 + tid) * 8;
+  Fr acc = Fr::zero();
+  if (base < len) {
+#pragma unroll
+    for (int k = 7; k >= 0; k--) {
+      const Fr c = (base + k < len) ? ld_fr_plain(poly, base + k) : Fr::zero();
+      acc = acc * x + c;
+    }
+  }
+  sh[tid][0] = make_uint4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
+  sh[tid][1] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
+  Fr pw = x.sqr().sqr().sqr();  // x^8: the weight of the neighbouring thread's value
+  __syncthreads();
+  for (int d = 1; d < 256; d <<= 1) {
+    if ((tid & (2 * d - 1)) == 0) {
+      const Fr v = lds_pair(sh[tid]) + lds_pair(sh[tid + d]) * pw;
+      sh[tid][0] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
+      sh[tid][1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+      pw = pw.sqr();
+    }
+    __syncthreads();
+  }
+  if (tid == 0) stg_fr(out_slot, 0, lds_pair(sh[0]));
+}
+
 struct EvalJobs {
   const uint4* poly[16];
   unsigned len[16];
@@ -435,41 +468,9 @@ struct EvalJobs {
   int njobs;
 };
 __global__ void __launch_bounds__(256) k_poly_eval(EvalJobs jobs, uint4* partial, unsigned nblocks) {
-  __shared__ uint4 sh[256][2];
-  const int j = blockIdx.y, tid = threadIdx.x;
-  const size_t base = ((size_t)blockIdx.x * 256 + tid) * 8;
-  const unsigned len = jobs.len[j];
-  Fr acc = Fr::zero();
-  if (base < len) {
-    const Fr x = jobs.point[j];
-#pragma unroll
-    for (int k = 7; k >= 0; k--) {
-      Fr c = (base + k < len) ? ld_fr_plain(jobs.poly[j], base + k) : Fr::zero();
-      acc = acc * x + c;
-    }
-    acc = acc * x.pow_u64(base);
-  }
-  sh[tid][0] = make_uint4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
-  sh[tid][1] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
-  __syncthreads();
-  for (int d = 128; d > 0; d >>= 1) {
-    if (tid < d) {
-      Fr v = lds_pair(sh[tid]) + lds_pair(sh[tid + d]);
-      sh[tid][0] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
-      sh[tid][1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
-    }
-    __syncthreads();
-  }
-  if (tid == 0) stg_fr(partial, (size_t)j * nblocks + blockIdx.x, lds_pair(sh[0]));
+  const int j = blockIdx.y;
+  cta_poly_eval(jobs.poly[j], jobs.len[j], jobs.point[j], partial + 2 * ((size_t)j * nblocks + blockIdx.x));
 }
-__global__ void k_sum_rows(const uint4* partial, unsigned nblocks, uint4* out) {
-  const int j = blockIdx.x;
-  if (threadIdx.x != 0) return;
-  Fr acc = Fr::zero();
-  for (unsigned b = 0; b < nblocks; b++) acc = acc + ld_fr_plain(partial, (size_t)j * nblocks + b);
-  stg_fr(out, j, acc);
-}
-
 // The same for one set of points and several polynomials laid out with a fixed stride: job (y, z) evaluates
 // base + z * row_stride at point[y]; partial is [z][y][nblocks].
 struct EvalRows {
@@ -479,33 +480,23 @@ struct EvalRows {
   Fr point[16];
 };
 __global__ void __launch_bounds__(256) k_poly_eval_rows(EvalRows jobs, uint4* partial, unsigned nblocks) {
-  __shared__ uint4 sh[256][2];
-  const int tid = threadIdx.x;
-  const size_t base = ((size_t)blockIdx.x * 256 + tid) * 8;
-  const uint4* poly = jobs.base + 2 * (size_t)blockIdx.z * jobs.row_stride;
-  const unsigned len = jobs.len;
+  cta_poly_eval(jobs.base + 2 * (size_t)blockIdx.z * jobs.row_stride, jobs.len, jobs.point[blockIdx.y],
+                partial + 2 * (((size_t)blockIdx.z * gridDim.y + blockIdx.y) * nblocks + blockIdx.x));
+}
+// out[j] = sum_blk partial[j][blk] x_j^(2048 blk), x_j = pts.p[j mod npts]: Horner over the blocks
+struct EvalPoints {
+  Fr p[16];
+};
+__global__ void k_sum_rows(const uint4* partial, unsigned nblocks, EvalPoints pts, int npts, uint4* out) {
+  const int j = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  Fr step = pts.p[j % npts];
+#pragma unroll 1
+  for (int k = 0; k < 11; k++) step = step.sqr();  // x^2048
   Fr acc = Fr::zero();
-  if (base < len) {
-    const Fr x = jobs.point[blockIdx.y];
-#pragma unroll
-    for (int k = 7; k >= 0; k--) {
-      Fr c = (base + k < len) ? ld_fr_plain(poly, base + k) : Fr::zero();
-      acc = acc * x + c;
-    }
-    acc = acc * x.pow_u64(base);
-  }
-  sh[tid][0] = make_uint4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
-  sh[tid][1] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
-  __syncthreads();
-  for (int d = 128; d > 0; d >>= 1) {
-    if (tid < d) {
-      Fr v = lds_pair(sh[tid]) + lds_pair(sh[tid + d]);
-      sh[tid][0] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
-      sh[tid][1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
-    }
-    __syncthreads();
-  }
-  if (tid == 0) stg_fr(partial, ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * nblocks + blockIdx.x, lds_pair(sh[0]));
+#pragma unroll 1
+  for (unsigned b = nblocks; b-- > 0;) acc = acc * step + ld_fr_plain(partial, (size_t)j * nblocks + b);
+  stg_fr(out, j, acc);
 }
 
 // Step 3 + 4 of the 4n-coset quotient (see prove_dev): thread j < 8 computes
@@ -691,7 +682,13 @@ static int prover_build(pb200_prover* P, const uint8_t* label, size_t label_len,
       for (int k = 0; k < 4 && e == cudaSuccess; k++)
         e = cudaMemcpyAsync(comb + 6 * (n + k), mono + 6 * idx[k], 96, cudaMemcpyDeviceToDevice, st);
       if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-      if (rc == 0 && e == cudaSuccess) rc = srs_from_device(comb, n + 4, &P->srs_lag);
+      // Window of the Lagrange-form key.  Its scalars are witness VALUES - mostly zero or a single small digit -
+      // so the bucket reduction (~2.3 additions per bucket whatever the scalars) outweighs the accumulation
+      // unless the window is narrower than the monomial key's: PB200_LAG_C overrides the default.
+      int lag_c = std::min(12, msm_window_for(n + 4));  // measured on BenchCircuit<2^16>: 12 bits 185 proofs/s, 16 bits 180
+      if (const char* env = getenv("PB200_LAG_C")) lag_c = atoi(env);
+      if (lag_c < 2 || lag_c > 20) lag_c = 0;
+      if (rc == 0 && e == cudaSuccess) rc = srs_from_device(comb, n + 4, &P->srs_lag, lag_c);
       cudaFree(comb);
       PB_TRY(rc);
       PB_CUDA(e);
@@ -1045,8 +1042,10 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
       EvalRows er;
       er.base = zp; er.row_stride = stride; er.len = (unsigned)n + 3;
       for (int j = 0; j < 16; j++) er.point[j] = qc.xs[j];
+      EvalPoints ep;
+      for (int j = 0; j < 16; j++) ep.p[j] = qc.xs[j];
       PB_LAUNCH(k_poly_eval_rows, dim3(eval_blocks, 16, rows), 256, 0, st, er, part4, eval_blocks);
-      PB_LAUNCH(k_sum_rows, 16 * rows, 32, 0, st, (const uint4*)part4, eval_blocks, wpts);
+      PB_LAUNCH(k_sum_rows, 16 * rows, 32, 0, st, (const uint4*)part4, eval_blocks, ep, 16, wpts);
     }
     if (!n_pi) PB_CUDA(cudaMemsetAsync(wpts + 2 * 16 * 5, 0, 16 * 32, st));
     QuotArgs qp = q;
@@ -1057,8 +1056,10 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
       EvalRows er;
       er.base = tcoef; er.row_stride = 0; er.len = (unsigned)n4;
       for (int j = 0; j < 16; j++) er.point[j] = qc.xs[j];
+      EvalPoints ep;
+      for (int j = 0; j < 16; j++) ep.p[j] = qc.xs[j];
       PB_LAUNCH(k_poly_eval_rows, dim3(blocks4, 8, 1), 256, 0, st, er, part4, blocks4);
-      PB_LAUNCH(k_sum_rows, 8, 32, 0, st, (const uint4*)part4, blocks4, ux);
+      PB_LAUNCH(k_sum_rows, 8, 32, 0, st, (const uint4*)part4, blocks4, ep, 16, ux);
     }
     // 3. t_hi(x_k) = (t(x_k) - u(x_k)) / (x_k^4n - g^4n), and x_k^4n = -g^4n for every k; the 8-point
     //    inverse DFT on h*H_8 gives its coefficients, the eighth of which must vanish (N divisible by Z_H:
@@ -1099,8 +1100,11 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
       jobs.len[j] = ls[j];
       jobs.point[j] = to_dev(shifted[j] ? zw : z_ch);
     }
+    EvalPoints ep;
+    for (int j = 0; j < 15; j++) ep.p[j] = jobs.point[j];
+    ep.p[15] = Fr::zero();
     PB_LAUNCH(k_poly_eval, dim3(eval_blocks, 15), 256, 0, st, jobs, partial, eval_blocks);
-    PB_LAUNCH(k_sum_rows, 15, 32, 0, st, (const uint4*)partial, eval_blocks, evals_d);
+    PB_LAUNCH(k_sum_rows, 15, 32, 0, st, (const uint4*)partial, eval_blocks, ep, 16, evals_d);
     PB_CUDA(cudaMemcpyAsync(stage, evals_d, 15 * 32, cudaMemcpyDeviceToHost, st));
     PB_CUDA(stream_wait(st));
     memcpy(ev, stage, 15 * 32);

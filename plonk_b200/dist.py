@@ -159,7 +159,8 @@ class ShardedCommitKey:
         L = lib()
         out = ctypes.create_string_buffer(G1_RAW_BYTES)
         if not self.uses_collective(n_scalars):
-            h = self._replica if self._replica else self._h
+            # the replica below the threshold; with a single rank the "slice" is the whole key
+            h = self._replica if (self._replica and n_scalars <= self.replica_points) else self._h
             check(L.pb200_msm_g1_dev(h, d_scalars, n_scalars, 1, max(n_scalars, 1), out, stream))
             return out.raw
         lo, cnt = self.slice_of(n_scalars)

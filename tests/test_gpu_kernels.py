@@ -243,21 +243,57 @@ def test_msm_2_20_points_against_known_secret(pb):
     assert pd.g1_sum(parts) == got.raw
 
 
-def test_msm_2_22_points_against_known_secret(pb):
-    """BASELINE.json configs[3] upper range on one GPU: 2^22 points, 20-bit windows.  The scalars are
-    64-bit-limb patterns cheap to build on the host; the result must equal [p(x)] g."""
+def _structured_msm_case(log_n, seed):
+    """n = 2^log_n distinct full-range scalars s_i = u[i mod 4096] + v[i div 4096] (mod r) whose polynomial has a
+    closed form, so that [p(x)]g is one scalar multiplication: p(x) = U(x) (x^n - 1)/(x^m - 1) + V(x^m) (x^m - 1)/(x - 1)."""
+    import torch
+
+    import bench
+
+    rng = random.Random(seed)
+    n, m = 1 << log_n, 4096
+    x, gs = rng.randrange(2, R.R_MOD), rng.randrange(1, R.R_MOD)
+    u, v = rand_fr(rng, m), rand_fr(rng, n // m)
+    scalars = bench.fr_outer_sum(torch, u, v).cpu().numpy().tobytes()
+    xm = pow(x, m, R.R_MOD)
+    geo_n = (pow(x, n, R.R_MOD) - 1) * pow(xm - 1, -1, R.R_MOD) % R.R_MOD
+    geo_m = (xm - 1) * pow(x - 1, -1, R.R_MOD) % R.R_MOD
+    px = (R.poly_eval(u, x) * geo_n + R.poly_eval(v, xm) * geo_m) % R.R_MOD
+    assert from_abi(scalars[: 32 * 3]) == [(a + v[0]) % R.R_MOD for a in u[:3]]
+    assert from_abi(scalars[32 * (m + 1) : 32 * (m + 2)]) == [(u[1] + v[1]) % R.R_MOD]
+    return n, x, gs, scalars, px
+
+
+@pytest.mark.parametrize("log_n", [22, 24])
+def test_msm_large_points_against_known_secret(pb, log_n):
+    """BASELINE.json configs[3] upper range on one GPU: 2^22 and 2^24 points, 20-bit windows, distinct
+    full-range scalars; the result must equal [p(x)] g."""
+    from plonk_b200._lib import check, lib
+
+    n, x, gs, scalars, px = _structured_msm_case(log_n, log_n)
+    assert len(scalars) == 32 * n
+    raw = ctypes.create_string_buffer(96 * n)
+    check(lib().pb200_srs_setup_from_secret(R.fr_to_mont_bytes(x), R.fr_to_mont_bytes(gs), n, raw))
+    key = pb.CommitKey(raw.raw)
+    del raw
+    got = key.commit(scalars)
+    assert R.g1_from_raw_bytes(got.raw) == R.g1_mul(R.g1_mul(R.G1_GEN, gs), px)
+
+
+def test_msm_repeated_scalar_block_is_skewed_but_exact(pb):
+    """A coefficient vector repeating one 4096-element block puts 256 entries into each of 53 000 of the 2^19
+    buckets and none into the rest: p(x) = B(x) * sum_j x^(4096 j)."""
     from plonk_b200._lib import check, lib
 
     rng = random.Random(22)
-    n = 1 << 22
+    n = 1 << 20
     x, gs = rng.randrange(1, R.R_MOD), rng.randrange(1, R.R_MOD)
     raw = ctypes.create_string_buffer(96 * n)
     check(lib().pb200_srs_setup_from_secret(R.fr_to_mont_bytes(x), R.fr_to_mont_bytes(gs), n, raw))
     key = pb.CommitKey(raw.raw)
     del raw
-    block = rand_fr(rng, 1 << 12)  # the coefficient vector repeats a 4096-element block: p(x) = B(x) * sum_j x^(4096 j)
-    scalars = to_abi(block) * (n >> 12)
-    got = key.commit(scalars)
+    block = rand_fr(rng, 1 << 12)
+    got = key.commit(to_abi(block) * (n >> 12))
     geo = (pow(x, n, R.R_MOD) - 1) * pow(pow(x, 1 << 12, R.R_MOD) - 1, -1, R.R_MOD) % R.R_MOD
     assert R.g1_from_raw_bytes(got.raw) == R.g1_mul(R.g1_mul(R.G1_GEN, gs), R.poly_eval(block, x) * geo % R.R_MOD)
 
