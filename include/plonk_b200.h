@@ -142,6 +142,22 @@ int pb200_srs_setup_from_secret(const uint64_t* x, const uint64_t* g_scalar, siz
  * 96-byte raw layout pb200_srs_upload / pb200_prover_new take.  The square roots and the subgroup
  * checks run on the GPU, one thread per point.  PB200_ERR_POINT_MALFORMED names the first bad point. */
 int pb200_g1_decompress(const uint8_t* compressed, size_t n_points, int check_subgroup, uint8_t* out_raw);
+/* The raw ("unchecked", fast-loading) key formats of the reference - SURVEY.md section 8 row f4.
+ *   CommitKey::to_raw_var_bytes (key.rs:215-229) = u64 little-endian point count, then per point
+ *   G1Affine::to_raw_bytes of dusk-bls12_381 0.14: PB200_G1_RAW_SIZE = 97 bytes = x then y as 6 + 6 little-endian
+ *   u64 Montgomery limbs (the first 96 bytes ARE this library's raw layout) and one byte that is 1 for the
+ *   identity.  That crate is not vendored under the reference checkout and the reference holds no golden bytes
+ *   for this format, so the record layout is restated from the crate's published source, not pinned by a vector.
+ *   PublicParameters::to_raw_var_bytes (srs.rs:114-119) = OpeningKey::to_bytes (PB200_OPENING_KEY_BYTES = 240: a
+ *   compressed G1 and two compressed G2 points, verifier material this library never reads) followed by the above.
+ * checked = 0 mirrors from_slice_unchecked (key.rs:242-256, srs.rs:132-146: no point validation, at most the
+ * announced count of whole records); checked = 1 mirrors CommitKey::from_raw_var_bytes (key.rs:258-298: exact
+ * length, is_on_curve & is_torsion_free per point - run on the GPU; PB200_ERR_POINT_MALFORMED names the first
+ * bad point).  out_raw receives n_points x 96 bytes for pb200_srs_upload / pb200_prover_new. */
+#define PB200_G1_RAW_SIZE 97
+#define PB200_OPENING_KEY_BYTES 240
+int pb200_raw_commit_key_points(const uint8_t* bytes, size_t len, int checked, size_t* n_points);
+int pb200_commit_key_from_raw_var_bytes(const uint8_t* bytes, size_t len, int checked, uint8_t* out_raw);
 /* 48-byte compressed encoding of one affine point given in the 96-byte raw layout. */
 int pb200_g1_compress(const uint64_t* affine_raw, uint8_t out48[48]);
 /* out = a + b for two points in the 96-byte raw layout (host-side helper for multi-GPU reduction). */
@@ -159,6 +175,21 @@ int pb200_g1_add_affine(const uint64_t* a_raw, const uint64_t* b_raw, uint64_t* 
 int pb200_prover_new(const uint8_t* label, size_t label_len, size_t n_constraints,
                      const uint64_t* selectors, const uint32_t* wires, size_t n_witnesses,
                      const uint8_t* srs_raw, size_t n_srs_points, pb200_prover_t** out);
+/* Prover::try_from_bytes (src/compiler/prover.rs:265-350) for the bytes of Prover::to_bytes (:236-263): six
+ * big-endian u64 (label, prover-key, commit-key, verifier-key lengths, size, constraints), the label,
+ * ProverKey::to_var_bytes (src/proof_system/widget.rs:347-445: n, the byte size of one Evaluations, then for
+ * each of the 15 polynomials its coefficient count, canonical 32-byte coefficients and its 8n coset
+ * evaluations, then the linear and vanishing-polynomial evaluations), the commit key in the raw format above
+ * and VerifierKey::to_bytes (widget.rs:84-111: n and 15 compressed commitments).  The polynomials go to HBM in
+ * coefficient form and the commitments are taken as stored, so none of the 15 iNTTs / 15 MSMs of preprocessing
+ * runs; the 8n evaluations are recomputed by 16 coset NTTs on the device (faster than moving 17 x 8n scalars
+ * over PCIe), so the serialized ones are skipped, not read.  Errors as the reference: too short ->
+ * PB200_ERR_INVALID_ARG (NotEnoughBytes), inconsistent sizes / non-canonical scalars -> PB200_ERR_POINT_MALFORMED
+ * (InvalidData), an invalid commit-key point -> PB200_ERR_POINT_MALFORMED (checked as try_from_bytes does).
+ * A serialized Prover does not hold the circuit's wiring (the reference re-runs the circuit per proof and reads
+ * the wires from that composer), so `wires` (4 x constraints witness indices) and n_witnesses come with it. */
+int pb200_prover_from_bytes(const uint8_t* bytes, size_t len, const uint32_t* wires, size_t n_witnesses,
+                            pb200_prover_t** out);
 void pb200_prover_free(pb200_prover_t* prover);
 /* 15 compressed commitments (verifier-key material) in the order of `selectors` then s_sigma_1..4. */
 int pb200_prover_commitments(const pb200_prover_t* prover, uint8_t* out_15x48);

@@ -103,9 +103,41 @@ int srs_window(const pb200_srs* s);
 int msm_window_for(size_t n_points);
 int srs_setup(const uint64_t* x_mont, const uint64_t* g_scalar_mont, size_t n, uint8_t* out_raw);
 int g1_decompress(const uint8_t* in, size_t n, int check_subgroup, uint8_t* out_raw);
+int g1_check_raw(const uint8_t* raw, size_t n);
+int raw_commit_key_parse(const uint8_t* bytes, size_t len, int checked, size_t* n_points, uint8_t* out_raw);
 extern std::atomic<int> g_prof_on;
 extern std::atomic<uint64_t> g_prof_acc_ns, g_prof_acc_adds, g_prof_acc_launches, g_prof_acc_points;
 void srs_free(pb200_srs* s);
+}  // namespace pb
+
+namespace pb {
+// checked = 1: CommitKey::from_raw_var_bytes (key.rs:258-298: the length must be exact, zero points are an
+// error); checked = 0: from_slice_unchecked (key.rs:242-256: as many whole records as the bytes hold, at most
+// the announced count).  Writes the 96-byte layout when out_raw is given (identity -> zeros).
+int raw_commit_key_parse(const uint8_t* bytes, size_t len, int checked, size_t* n_points, uint8_t* out_raw) {
+  if (len < 8) return fail(PB200_ERR_INVALID_ARG, "NotEnoughBytes: raw commit key shorter than its length prefix");
+  uint64_t cnt = 0;
+  for (int i = 7; i >= 0; i--) cnt = (cnt << 8) | bytes[i];
+  const size_t have = (len - 8) / PB200_G1_RAW_SIZE;
+  size_t n;
+  if (checked) {
+    if (cnt == 0) return fail(PB200_ERR_POINT_MALFORMED, "InvalidData: empty commit key");
+    if (cnt > have || (len - 8) != (size_t)cnt * PB200_G1_RAW_SIZE) return fail(PB200_ERR_INVALID_ARG, "NotEnoughBytes: raw commit key length does not match its point count");
+    n = (size_t)cnt;
+  } else {
+    n = cnt < have ? (size_t)cnt : have;
+  }
+  *n_points = n;
+  if (out_raw)
+    for (size_t i = 0; i < n; i++) {
+      const uint8_t* rec = bytes + 8 + i * PB200_G1_RAW_SIZE;
+      if (rec[96])
+        memset(out_raw + 96 * i, 0, 96);  // Choice(1): the identity, whatever its coordinates hold
+      else
+        memcpy(out_raw + 96 * i, rec, 96);
+    }
+  return 0;
+}
 }  // namespace pb
 
 using namespace pb;
@@ -311,6 +343,23 @@ int pb200_g1_decompress(const uint8_t* compressed, size_t n_points, int check_su
   if (!compressed || !out_raw) return fail(PB200_ERR_INVALID_ARG, "null argument");
   if (!n_points) return 0;
   return g1_decompress(compressed, n_points, check_subgroup, out_raw);
+}
+
+// CommitKey::to_raw_var_bytes (key.rs:215-229): u64 LE point count, then per point G1Affine::to_raw_bytes of
+// dusk-bls12_381 0.14 - RAW_SIZE = 97: x, y as 6 + 6 little-endian u64 Montgomery limbs and one infinity byte.
+int pb200_raw_commit_key_points(const uint8_t* bytes, size_t len, int checked, size_t* n_points) {
+  if (!bytes || !n_points) return fail(PB200_ERR_INVALID_ARG, "null argument");
+  return raw_commit_key_parse(bytes, len, checked, n_points, nullptr);
+}
+int pb200_commit_key_from_raw_var_bytes(const uint8_t* bytes, size_t len, int checked, uint8_t* out_raw) {
+  if (!bytes || !out_raw) return fail(PB200_ERR_INVALID_ARG, "null argument");
+  size_t n = 0;
+  PB_TRY(raw_commit_key_parse(bytes, len, checked, &n, out_raw));
+  if (checked) {
+    PB_TRY(ensure_init());
+    PB_TRY(g1_check_raw(out_raw, n));
+  }
+  return 0;
 }
 
 int pb200_srs_setup_from_secret(const uint64_t* x, const uint64_t* g_scalar, size_t n_points, uint8_t* out_raw) {

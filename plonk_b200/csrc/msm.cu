@@ -218,6 +218,33 @@ __global__ void __launch_bounds__(64) k_g1_decompress(const uint8_t* in, size_t 
   st_affine(out, i, pt);
 }
 
+// CommitKey::from_raw_var_bytes (reference src/commitment_scheme/kzg10/key.rs:258-298) validates every
+// point of a raw-encoded key with is_on_curve() & is_torsion_free(); this is that check for points already
+// in the 96-byte raw layout (identity = zeros, always valid).  One thread per point; `bad` receives the
+// smallest index of an invalid point.
+__global__ void __launch_bounds__(64) k_g1_check_raw(const uint4* pts, size_t n, unsigned* bad) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const G1Affine p = ld_affine(pts, i);
+  if (p.is_inf()) return;
+  const Fp four = Fp::one().dbl().dbl();
+  bool ok = p.y.sqr() == p.x.sqr() * p.x + four;
+  if (ok) {
+    G1Xyzz acc = G1Xyzz::identity();
+#pragma unroll 1
+    for (int w = 7; w >= 0; w--) {
+      const uint32_t word = FrParams::MOD(w);
+#pragma unroll 1
+      for (int bit = 31; bit >= 0; bit--) {
+        acc = xyzz_dbl(acc);
+        if ((word >> bit) & 1u) xyzz_madd(acc, p.x, p.y);
+      }
+    }
+    ok = acc.is_inf();
+  }
+  if (!ok) atomicMin(bad, (unsigned)i);
+}
+
 // Signed-digit recoding + bucket histogram.  ebkt/epos are [batch][W][n].
 __global__ void k_msm_digits(const uint4* scalars, size_t n, size_t stride, int c, int W, unsigned nb,
                              unsigned* counts, unsigned* ebkt, unsigned* epos) {
@@ -996,6 +1023,17 @@ struct MsmTail {
   size_t words_per_entry() const { return (size_t)(plan.ndig + 1) * 48; }  // 32-bit words of one batch entry
 };
 
+// pair slots (running product + descriptor) per batch entry: the widest round's thread count x kAffK / 2
+static size_t aff_slots(size_t cap, size_t nb) {
+  size_t widest = 0;
+  for (int r = 0; ((size_t)1 << r) < cap || r == 0; r++) {
+    const size_t positions = r == 0 ? cap : (cap >> r) + nb + 1;
+    const size_t ctas = ((positions + kAffK - 1) / kAffK + kAffThreads - 1) / kAffThreads;
+    widest = std::max(widest, ctas * kAffThreads);
+  }
+  return widest * (kAffK / 2);
+}
+
 static int msm_plan_c(int c, uint32_t batch, MsmTail* tail, unsigned* n_groups_out, int* g_out) {
   const unsigned nb = 1u << (c - 1);
   const int g = std::min<unsigned>(kGroup, nb);
@@ -1100,8 +1138,11 @@ static int msm_enqueue(const pb200_srs* srs, size_t first, const uint64_t* d_sca
   if (affine) {
     // batched-affine pairwise rounds (see k_msm_affine_round)
     const size_t capA = cap / 2 + nb + 2, capB = cap / 4 + nb + 2;
-    const unsigned threads0 = div_up(div_up(cap, kAffK), kAffThreads) * kAffThreads;
-    const size_t slots = (size_t)threads0 * (kAffK / 2);
+    int rounds = 0;
+    while (((size_t)1 << rounds) < cap) rounds++;  // a bucket can hold every entry (equal scalars with equal digits)
+    // input positions of round r: layout 0 is exact, layout r >= 1 has at most one slot of slack per bucket
+    auto positions = [&](int r) { return r == 0 ? cap : (cap >> r) + nb + 1; };
+    const size_t slots = aff_slots(cap, nb);
     uint4 *bufA = nullptr, *bufB = nullptr, *pre = nullptr;
     uint2* desc = nullptr;
     PB_ALLOC(scope, bufA, (size_t)batch * capA * 96);
@@ -1109,8 +1150,6 @@ static int msm_enqueue(const pb200_srs* srs, size_t first, const uint64_t* d_sca
     PB_ALLOC(scope, pre, (size_t)batch * slots * 48);
     PB_ALLOC(scope, desc, (size_t)batch * slots * 8);
     PB_CUDA(cudaMemsetAsync(sums, 0, (size_t)batch * nb * 96, st));
-    int rounds = 0;
-    while (((size_t)1 << rounds) < cap) rounds++;  // a bucket can hold every entry (equal scalars with equal digits)
     for (int r = 0; r < rounds; r++) {
       AffRound a;
       a.table = srs->table; a.sorted = sorted; a.offsets = offsets; a.max_len = max_len; a.prefix = pre; a.desc = desc; a.sums = sums;
@@ -1119,8 +1158,7 @@ static int msm_enqueue(const pb200_srs* srs, size_t first, const uint64_t* d_sca
       a.out = (r & 1) ? bufB : bufA;  // layout r + 1
       a.in_cap = (r & 1) ? capA : capB;
       a.out_cap = (r & 1) ? capB : capA;
-      const size_t positions = (cap >> r) + nb + 1;
-      const unsigned ctas = div_up(div_up(positions, kAffK), kAffThreads);
+      const unsigned ctas = div_up(div_up(positions(r), kAffK), kAffThreads);
       a.threads = ctas * kAffThreads;
       a.slots = slots;
       if (r == 0)
@@ -1369,9 +1407,8 @@ size_t msm_workspace_bytes(const pb200_srs* srs, size_t n, uint32_t batch) {
   b += (size_t)batch * (8 * 16 + n_groups / 256 + 2) * (n_groups / (16 * kClassChunk) + 2) * 192 + 256;  // classes x chunks
   b += (size_t)batch * 9 * 192 + 256;                  // result
   {  // batched-affine rounds: two point buffers, running products, pair descriptors
-    const size_t threads0 = ((cap + kAffK - 1) / kAffK + kAffThreads - 1) / kAffThreads * kAffThreads;
     b += (size_t)batch * ((cap / 2 + nb + 2) + (cap / 4 + nb + 2)) * 96 + 512;
-    b += (size_t)batch * threads0 * (kAffK / 2) * (48 + 8) + 512;
+    b += (size_t)batch * aff_slots(cap, nb) * (48 + 8) + 512;
   }
   return b + 4096;
 }
@@ -1476,6 +1513,33 @@ int g1_decompress(const uint8_t* in, size_t n, int check_subgroup, uint8_t* out_
     char msg[64];
     snprintf(msg, sizeof msg, "point %u", bad);
     return fail(PB200_ERR_POINT_MALFORMED, "malformed G1 encoding (not canonical, not on the curve or not in the subgroup)", msg);
+  }
+  return 0;
+}
+
+int g1_check_raw(const uint8_t* raw, size_t n) {
+  if (!n) return 0;
+  cudaStream_t st = thread_stream();
+  uint4* d = nullptr;
+  unsigned* d_bad = nullptr;
+  PB_CUDA(cudaMalloc((void**)&d, n * 96));
+  cudaError_t e = cudaMalloc((void**)&d_bad, 4);
+  unsigned bad = 0xffffffffu;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d, raw, n * 96, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0xff, 4, st);
+  if (e == cudaSuccess) {
+    PB_LAUNCH(k_g1_check_raw, div_up(n, 64), 64, 0, st, (const uint4*)d, n, d_bad);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  cudaFree(d_bad);
+  PB_CUDA(e);
+  if (bad != 0xffffffffu) {
+    char msg[64];
+    snprintf(msg, sizeof msg, "point %u", bad);
+    return fail(PB200_ERR_POINT_MALFORMED, "commit-key point not on the curve or not in the prime-order subgroup (PointMalformed)", msg);
   }
   return 0;
 }

@@ -40,6 +40,8 @@ size_t srs_len(const pb200_srs* s);
 const uint4* srs_points(const pb200_srs* s);
 int srs_from_device(const uint4* d_points, size_t n_points, pb200_srs** out, int window_bits);
 int msm_window_for(size_t n_points);
+int g1_check_raw(const uint8_t* raw, size_t n);
+int raw_commit_key_parse(const uint8_t* bytes, size_t len, int checked, size_t* n_points, uint8_t* out_raw);
 int lagrange_key_dev(const uint4* d_in, int log_n, uint4* d_out, cudaStream_t st);
 int get_twiddles(int logm, bool inverse, cudaStream_t st, const uint4** out);
 int fill_powers(uint4* out, size_t n, const Fr& base, const Fr& scale, cudaStream_t st);
@@ -114,6 +116,25 @@ __global__ void k_blind(uint4* polys, size_t stride, size_t n, BlindArgs a) {
   uint4* c = polys + 2 * (size_t)p * stride;
   stg_fr(c, i, ld_fr_plain(c, i) - a.b[p][i]);
   stg_fr(c, n + i, a.b[p][i]);
+}
+
+// BlsScalar::from_bytes for a whole array (canonical little-endian integers -> Montgomery form); a value
+// >= r is not canonical and raises `flag` (dusk_bytes::Error::InvalidData in the reference).
+__global__ void k_fr_from_canonical(uint4* p, size_t n_elems, unsigned* flag) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_elems) return;
+  const Fr x = ld_fr_plain(p, i);
+  bool lt = false;
+#pragma unroll
+  for (int k = 7; k >= 0; k--) {
+    const uint32_t m = FrParams::MOD(k);
+    if (x.v[k] != m) {
+      lt = x.v[k] < m;
+      break;
+    }
+  }
+  if (!lt) atomicOr(flag, 1u);
+  stg_fr(p, i, x.to_mont());
 }
 
 __global__ void k_zero(uint4* p, size_t n_elems) {
@@ -388,7 +409,10 @@ __global__ void __launch_bounds__(128) k_quotient(QuotArgs q) {
   quotient_point(q, q.n8, i, (i + 8) & (q.n8 - 1), i, i);
 }
 // The same on the 4n coset g*H_4n = the even points of the 8n coset (PB200_QUOT4N=1, see prove_dev).
-__global__ void __launch_bounds__(128) k_quotient_4n(QuotArgs q) {
+// MINB = resident CTAs per SM the register allocation is made for: 2 -> 240 registers, no spills; 3 -> 168
+// registers and ~300 bytes of spills per thread (PB200_QUOT_OCC selects; measured).
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_quotient_4n(QuotArgs q) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t n4 = q.n8 >> 1;
   if (i >= n4) return;
@@ -647,8 +671,17 @@ struct PoolBlock {
   PoolBlock& operator=(const PoolBlock&) = delete;
 };
 
+// A prover key read from Prover::to_bytes: coefficient-form polynomials (canonical scalars) and commitments,
+// both already in this file's enum order.
+struct LoadedProverKey {
+  const uint8_t* poly[N_POLY];
+  size_t poly_len[N_POLY];
+  uint8_t comm[N_POLY][48];
+};
+
 static int prover_build(pb200_prover* P, const uint8_t* label, size_t label_len, size_t constraints, const uint64_t* selectors,
-                        const uint32_t* wires, size_t n_witnesses, const uint8_t* srs_raw, size_t n_srs, cudaStream_t st) {
+                        const uint32_t* wires, size_t n_witnesses, const uint8_t* srs_raw, size_t n_srs, cudaStream_t st,
+                        const LoadedProverKey* loaded = nullptr) {
   P->label.assign(label, label + label_len);
   P->constraints = constraints;
   P->n_witnesses = n_witnesses;
@@ -703,48 +736,72 @@ static int prover_build(pb200_prover* P, const uint8_t* label, size_t label_len,
   PB_CUDA(cudaMalloc((void**)&P->d_sigma, 4 * n * 32));
   PB_CUDA(cudaMemcpyAsync(P->d_wires, wires, 4 * constraints * 4, cudaMemcpyHostToDevice, st));
 
-  // selector columns, zero padded to n, then iNTT -> coefficient form (compiler.rs:149-211)
-  PoolBlock cols_block(st);
-  PB_CUDA(cols_block.alloc((size_t)N_POLY * n * 32));
-  uint4* cols = (uint4*)cols_block.p;
-  PB_CUDA(cudaMemsetAsync(cols, 0, (size_t)N_POLY * n * 32, st));
-  PB_CUDA(cudaMemcpy2DAsync(cols, n * 32, selectors, constraints * 32, constraints * 32, 11, cudaMemcpyHostToDevice, st));
-  // sigma permutation on the host (composer/permutation.rs:106-141), Lagrange values on the device
-  {
-    std::vector<std::vector<uint64_t>> wmap(n_witnesses);
+  if (loaded) {
+    // Prover::try_from_bytes: the polynomials arrive in coefficient form and the commitments as stored - no
+    // interpolation, no MSM
     for (size_t g = 0; g < constraints; g++)
-      for (int k = 0; k < 4; k++) {
-        const uint32_t w = wires[(size_t)k * constraints + g];
-        if (w >= n_witnesses) {
-          return fail(PB200_ERR_INVALID_ARG, "wire index out of range");
-        }
-        wmap[w].push_back(((uint64_t)k << 40) | g);
-      }
-    std::vector<unsigned long long> sig(4 * n);
-    for (int k = 0; k < 4; k++)
-      for (size_t i = 0; i < n; i++) sig[(size_t)k * n + i] = ((uint64_t)k << 40) | i;
-    for (auto& lst : wmap)
-      for (size_t i = 0; i < lst.size(); i++) {
-        const uint64_t cur = lst[i], nxt = lst[(i + 1) % lst.size()];
-        sig[(size_t)(cur >> 40) * n + (cur & 0xffffffffffull)] = nxt;
-      }
-    PoolBlock sig_block(st);
-    PB_CUDA(sig_block.alloc(4 * n * 8));
-    unsigned long long* d_sig = (unsigned long long*)sig_block.p;
-    PB_CUDA(cudaMemcpyAsync(d_sig, sig.data(), 4 * n * 8, cudaMemcpyHostToDevice, st));
-    const uint4* w_half = nullptr;
-    PB_TRY(get_twiddles(log_n, false, st, &w_half));
-    PB_LAUNCH(k_sigma_lagrange, div_up(4 * n, 256), 256, 0, st, d_sig, n, w_half, cols + 2 * (size_t)S1 * n);
-    PB_CUDA(cudaStreamSynchronize(st));  // sig (host vector) must outlive the copy
-  }
-  PB_TRY(ntt_run((const uint64_t*)cols, n, (uint64_t*)P->d_polys, log_n, 1, 0, N_POLY, n, n, st, nullptr));
-  // commitments (compiler.rs:213-232): an all-zero selector commits to the identity
-  {
-    std::vector<uint64_t> aff((size_t)N_POLY * 12);
-    PB_TRY(msm_run(P->srs, 0, (const uint64_t*)P->d_polys, n, N_POLY, n, aff.data(), st, nullptr));
-    for (int k = 0; k < N_POLY; k++) compress_affine(aff.data() + 12 * k, P->comm[k]);
+      for (int k = 0; k < 4; k++)
+        if (wires[(size_t)k * constraints + g] >= n_witnesses) return fail(PB200_ERR_INVALID_ARG, "wire index out of range");
+    PB_CUDA(cudaMemsetAsync(P->d_polys, 0, (size_t)N_POLY * n * 32, st));
+    for (int k = 0; k < N_POLY; k++)
+      if (loaded->poly_len[k])
+        PB_CUDA(cudaMemcpyAsync(P->d_polys + 2 * (size_t)k * n, loaded->poly[k], loaded->poly_len[k] * 32, cudaMemcpyHostToDevice, st));
+    PoolBlock flag_block(st);
+    PB_CUDA(flag_block.alloc(4));
+    unsigned* d_flag = (unsigned*)flag_block.p;
+    PB_CUDA(cudaMemsetAsync(d_flag, 0, 4, st));
+    PB_LAUNCH(k_fr_from_canonical, div_up((size_t)N_POLY * n, 256), 256, 0, st, P->d_polys, (size_t)N_POLY * n, d_flag);
+    unsigned h_flag = 0;
+    PB_CUDA(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    if (h_flag) return fail(PB200_ERR_POINT_MALFORMED, "InvalidData: a prover-key scalar is not canonical");
+    memcpy(P->comm, loaded->comm, sizeof P->comm);
     const int widget_sel[4] = {Q_RANGE, Q_LOGIC, Q_FIXED, Q_VAR};
     for (int w = 0; w < 4; w++) P->has_widget[w] = (P->comm[widget_sel[w]][0] & 0x40) ? 0 : 1;
+  } else {
+    // selector columns, zero padded to n, then iNTT -> coefficient form (compiler.rs:149-211)
+    PoolBlock cols_block(st);
+    PB_CUDA(cols_block.alloc((size_t)N_POLY * n * 32));
+    uint4* cols = (uint4*)cols_block.p;
+    PB_CUDA(cudaMemsetAsync(cols, 0, (size_t)N_POLY * n * 32, st));
+    PB_CUDA(cudaMemcpy2DAsync(cols, n * 32, selectors, constraints * 32, constraints * 32, 11, cudaMemcpyHostToDevice, st));
+    // sigma permutation on the host (composer/permutation.rs:106-141), Lagrange values on the device
+    {
+      std::vector<std::vector<uint64_t>> wmap(n_witnesses);
+      for (size_t g = 0; g < constraints; g++)
+        for (int k = 0; k < 4; k++) {
+          const uint32_t w = wires[(size_t)k * constraints + g];
+          if (w >= n_witnesses) {
+            return fail(PB200_ERR_INVALID_ARG, "wire index out of range");
+          }
+          wmap[w].push_back(((uint64_t)k << 40) | g);
+        }
+      std::vector<unsigned long long> sig(4 * n);
+      for (int k = 0; k < 4; k++)
+        for (size_t i = 0; i < n; i++) sig[(size_t)k * n + i] = ((uint64_t)k << 40) | i;
+      for (auto& lst : wmap)
+        for (size_t i = 0; i < lst.size(); i++) {
+          const uint64_t cur = lst[i], nxt = lst[(i + 1) % lst.size()];
+          sig[(size_t)(cur >> 40) * n + (cur & 0xffffffffffull)] = nxt;
+        }
+      PoolBlock sig_block(st);
+      PB_CUDA(sig_block.alloc(4 * n * 8));
+      unsigned long long* d_sig = (unsigned long long*)sig_block.p;
+      PB_CUDA(cudaMemcpyAsync(d_sig, sig.data(), 4 * n * 8, cudaMemcpyHostToDevice, st));
+      const uint4* w_half = nullptr;
+      PB_TRY(get_twiddles(log_n, false, st, &w_half));
+      PB_LAUNCH(k_sigma_lagrange, div_up(4 * n, 256), 256, 0, st, d_sig, n, w_half, cols + 2 * (size_t)S1 * n);
+      PB_CUDA(cudaStreamSynchronize(st));  // sig (host vector) must outlive the copy
+    }
+    PB_TRY(ntt_run((const uint64_t*)cols, n, (uint64_t*)P->d_polys, log_n, 1, 0, N_POLY, n, n, st, nullptr));
+    // commitments (compiler.rs:213-232): an all-zero selector commits to the identity
+    {
+      std::vector<uint64_t> aff((size_t)N_POLY * 12);
+      PB_TRY(msm_run(P->srs, 0, (const uint64_t*)P->d_polys, n, N_POLY, n, aff.data(), st, nullptr));
+      for (int k = 0; k < N_POLY; k++) compress_affine(aff.data() + 12 * k, P->comm[k]);
+      const int widget_sel[4] = {Q_RANGE, Q_LOGIC, Q_FIXED, Q_VAR};
+      for (int w = 0; w < 4; w++) P->has_widget[w] = (P->comm[widget_sel[w]][0] & 0x40) ? 0 : 1;
+    }
   }
   // coset evaluations over 8n (compiler.rs:306-377)
   PB_TRY(ntt_run((const uint64_t*)P->d_polys, n, (uint64_t*)P->d_key8, log_n + 3, 0, 1, N_POLY, n, n8, st, nullptr));
@@ -818,6 +875,79 @@ int prover_new(const uint8_t* label, size_t label_len, size_t constraints, const
   const int rc = prover_build(P, label, label_len, constraints, selectors, wires, n_witnesses, srs_raw, n_srs, thread_stream());
   if (rc != 0) {
     prover_free(P);  // releases whatever had been allocated; the error message is already set
+    return rc;
+  }
+  *out = P;
+  return 0;
+}
+
+// Prover::try_from_bytes (src/compiler/prover.rs:265-350); the layout is spelled out at pb200_prover_from_bytes
+// in include/plonk_b200.h.
+int prover_from_bytes(const uint8_t* bytes, size_t len, const uint32_t* wires, size_t n_witnesses, pb200_prover** out) {
+  auto be64 = [](const uint8_t* p) {
+    uint64_t v = 0;
+    for (int i = 0; i < 8; i++) v = (v << 8) | p[i];
+    return v;
+  };
+  auto le64 = [](const uint8_t* p) {
+    uint64_t v = 0;
+    for (int i = 7; i >= 0; i--) v = (v << 8) | p[i];
+    return v;
+  };
+  const int short_rc = PB200_ERR_INVALID_ARG, bad_rc = PB200_ERR_POINT_MALFORMED;
+  if (len < 48) return fail(short_rc, "NotEnoughBytes: serialized prover shorter than its header");
+  const uint64_t label_len = be64(bytes), pk_len = be64(bytes + 8), ck_len = be64(bytes + 16), vk_len = be64(bytes + 24),
+                 size = be64(bytes + 32), constraints = be64(bytes + 40);
+  const uint8_t* p = bytes + 48;
+  size_t left = len - 48;
+  if (label_len > left || pk_len > left - label_len || ck_len > left - label_len - pk_len || vk_len > left - label_len - pk_len - ck_len)
+    return fail(short_rc, "NotEnoughBytes: serialized prover shorter than its sections");
+  size_t pow2 = 1;
+  while (pow2 < constraints) pow2 <<= 1;
+  if (constraints == 0 || pow2 != size) return fail(bad_rc, "InvalidData: size is not the next power of two of the constraint count");
+  const uint8_t* label = p;
+  const uint8_t* pk = label + label_len;
+  const uint8_t* ck = pk + pk_len;
+  const uint8_t* vk = ck + ck_len;
+  // ProverKey::to_var_bytes (widget.rs:347-445); file order of the 15 polynomials -> this file's enum
+  static const int file_order[N_POLY] = {Q_M, Q_L, Q_R, Q_O, Q_F, Q_C, Q_ARITH, Q_LOGIC, Q_RANGE, Q_FIXED, Q_VAR, S1, S2, S3, S4};
+  LoadedProverKey key;
+  {
+    size_t off = 0;
+    auto need = [&](size_t k) { return k <= pk_len - off; };
+    if (pk_len < 16) return fail(short_rc, "NotEnoughBytes: prover key");
+    const uint64_t n = le64(pk), eval_size = le64(pk + 8);
+    off = 16;
+    if (n != size) return fail(bad_rc, "InvalidData: prover key domain differs from the prover's size");
+    if (eval_size != 8 * n * 32 + 172) return fail(bad_rc, "InvalidData: evaluations are not over the 8n domain");
+    for (int i = 0; i < N_POLY; i++) {
+      if (!need(8)) return fail(short_rc, "NotEnoughBytes: prover key polynomial header");
+      const uint64_t cnt = le64(pk + off);
+      off += 8;
+      if (cnt > n) return fail(bad_rc, "InvalidData: polynomial longer than the domain");
+      if (!need(cnt * 32)) return fail(short_rc, "NotEnoughBytes: prover key polynomial");
+      key.poly[file_order[i]] = pk + off;
+      key.poly_len[file_order[i]] = (size_t)cnt;
+      off += cnt * 32;
+      if (!need(eval_size)) return fail(short_rc, "NotEnoughBytes: prover key evaluations");
+      off += eval_size;  // recomputed on the device
+    }
+    if (!need(2 * eval_size)) return fail(short_rc, "NotEnoughBytes: linear / vanishing evaluations");
+  }
+  // VerifierKey::to_bytes (widget.rs:84-111)
+  if (vk_len < 8 + 15 * 48) return fail(short_rc, "NotEnoughBytes: verifier key");
+  if (le64(vk) != size) return fail(bad_rc, "InvalidData: verifier key domain differs from the prover's size");
+  for (int i = 0; i < N_POLY; i++) memcpy(key.comm[file_order[i]], vk + 8 + 48 * i, 48);
+  // CommitKey::from_raw_var_bytes: validated points
+  size_t n_pts = 0;
+  PB_TRY(raw_commit_key_parse(ck, ck_len, 1, &n_pts, nullptr));
+  std::vector<uint8_t> raw(n_pts * 96);
+  PB_TRY(raw_commit_key_parse(ck, ck_len, 1, &n_pts, raw.data()));
+  PB_TRY(g1_check_raw(raw.data(), n_pts));
+  pb200_prover* P = new pb200_prover();
+  const int rc = prover_build(P, label, label_len, constraints, nullptr, wires, n_witnesses, raw.data(), n_pts, thread_stream(), &key);
+  if (rc != 0) {
+    prover_free(P);
     return rc;
   }
   *out = P;
@@ -1026,7 +1156,14 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
     // 1. u(X) = t(X) mod (X^4n - g^4n) from the 4n coset
     PB_TRY(ntt_run((const uint64_t*)zp, n + 3, (uint64_t*)w8, log_n + 2, 0, 1, n_pi ? 6 : 5, stride, n4, st, ar));
     if (!n_pi) PB_CUDA(cudaMemsetAsync(w8 + 2 * 5 * n4, 0, n4 * 32, st));
-    PB_LAUNCH(k_quotient_4n, div_up(n4, 128), 128, 0, st, q);
+    static const int quot_occ = [] {
+      const char* e = getenv("PB200_QUOT_OCC");
+      return e ? atoi(e) : 3;  // measured: 195.9 proofs/s at 3 CTAs/SM (168 registers, ~300 B spilled) against 194.0 at 2
+    }();
+    if (quot_occ == 3)
+      PB_LAUNCH(k_quotient_4n<3>, div_up(n4, 128), 128, 0, st, q);
+    else
+      PB_LAUNCH(k_quotient_4n<2>, div_up(n4, 128), 128, 0, st, q);
     PB_TRY(ntt_run((const uint64_t*)quot, n4, (uint64_t*)tcoef, log_n + 2, 1, 1, 1, n4, n4, st, ar));
     // 2. t at the eight points x_k = h w8^k, h = g w_8n (indices 1 + n k of the 8n coset): the witness
     //    polynomials by Horner at x_k and omega x_k, the prover key from its 8n tables.  The upper half
@@ -1249,6 +1386,12 @@ int pb200_prover_new(const uint8_t* label, size_t label_len, size_t n_constraint
   PB_TRY(ensure_init());
   if (!selectors || !wires || !srs_raw || !out) return fail(PB200_ERR_INVALID_ARG, "null argument");
   return prover_new(label, label_len, n_constraints, selectors, wires, n_witnesses, srs_raw, n_srs_points, out);
+}
+
+int pb200_prover_from_bytes(const uint8_t* bytes, size_t len, const uint32_t* wires, size_t n_witnesses, pb200_prover_t** out) {
+  PB_TRY(ensure_init());
+  if (!bytes || !wires || !out) return fail(PB200_ERR_INVALID_ARG, "null argument");
+  return prover_from_bytes(bytes, len, wires, n_witnesses, out);
 }
 
 void pb200_prover_free(pb200_prover_t* p) { prover_free(p); }

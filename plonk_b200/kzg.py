@@ -34,6 +34,25 @@ def g1_decompress(compressed: bytes, check_subgroup: bool = True) -> bytes:
     return out.raw[: n * G1_RAW_BYTES]
 
 
+def _raw_key_points(blob: bytes, checked: bool) -> bytes:
+    n = ctypes.c_size_t()
+    try:
+        check(lib().pb200_raw_commit_key_points(blob, len(blob), 1 if checked else 0, ctypes.byref(n)))
+        out = ctypes.create_string_buffer(max(n.value, 1) * G1_RAW_BYTES)
+        check(lib().pb200_commit_key_from_raw_var_bytes(blob, len(blob), 1 if checked else 0, out))
+    except Pb200Error as e:
+        if e.code == PB200_ERR_POINT_MALFORMED:
+            raise PointMalformed(str(e)) from e
+        raise
+    return out.raw[: n.value * G1_RAW_BYTES]
+
+
+def commit_key_bytes_of_public_parameters(raw_var_bytes: bytes) -> bytes:
+    """PublicParameters::to_raw_var_bytes (srs.rs:114-119) = OpeningKey::to_bytes (240 bytes: a compressed G1 and
+    two compressed G2 points, verifier material) followed by CommitKey::to_raw_var_bytes: returns the latter."""
+    return raw_var_bytes[240:]
+
+
 def g1_compress(raw_points: bytes) -> bytes:
     out = ctypes.create_string_buffer(48)
     res = bytearray()
@@ -74,6 +93,16 @@ class CommitKey:
     def from_slice(cls, compressed: bytes) -> "CommitKey":
         """CommitKey::from_slice (key.rs:319-326): 48-byte compressed powers, validated like the reference."""
         return cls(g1_decompress(compressed))
+
+    @classmethod
+    def from_raw_var_bytes(cls, raw_var_bytes: bytes) -> "CommitKey":
+        """CommitKey::from_raw_var_bytes (key.rs:258-298): the raw format with every point validated (on the GPU)."""
+        return cls(_raw_key_points(raw_var_bytes, True))
+
+    @classmethod
+    def from_slice_unchecked(cls, raw_var_bytes: bytes) -> "CommitKey":
+        """CommitKey::from_slice_unchecked (key.rs:242-256): the raw format from a trusted source, no validation."""
+        return cls(_raw_key_points(raw_var_bytes, False))
 
     def max_degree(self) -> int:
         return self.n_points - 1

@@ -27,6 +27,18 @@ class Prover:
         self.n_constraints = n_constraints
         self.n_witnesses = n_witnesses
 
+    @classmethod
+    def from_bytes(cls, prover_bytes: bytes, wires: bytes, n_witnesses: int) -> "Prover":
+        """Prover::try_from_bytes (prover.rs:265-350) for the output of Prover::to_bytes; the circuit's wiring
+        (4 x constraints u32) is not part of that format and comes alongside."""
+        self = cls.__new__(cls)
+        h = ctypes.c_void_p()
+        check(lib().pb200_prover_from_bytes(prover_bytes, len(prover_bytes), wires, n_witnesses, ctypes.byref(h)))
+        self._h = h
+        self.n_constraints = len(wires) // 16
+        self.n_witnesses = n_witnesses
+        return self
+
     def commitments(self):
         out = ctypes.create_string_buffer(15 * 48)
         check(lib().pb200_prover_commitments(self._h, out))
