@@ -18,6 +18,7 @@
 #include <array>
 #include <cstdint>
 #include <stdexcept>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -94,6 +95,10 @@ class CommitKey {
  public:
   // powers_of_g as 96-byte raw points (CommitKey::to_raw_var_bytes without length prefix / flags)
   CommitKey(const uint8_t* raw_points, size_t n_points) : n_(n_points) { check(pb200_srs_upload(raw_points, n_points, &h_)); }
+  // CommitKey::from_raw_var_bytes (key.rs:258-298: every point validated, on the GPU) and
+  // CommitKey::from_slice_unchecked (key.rs:242-256: trusted bytes) for CommitKey::to_raw_var_bytes
+  static std::unique_ptr<CommitKey> from_raw_var_bytes(const uint8_t* bytes, size_t len) { return from_raw(bytes, len, 1); }
+  static std::unique_ptr<CommitKey> from_slice_unchecked(const uint8_t* bytes, size_t len) { return from_raw(bytes, len, 0); }
   ~CommitKey() { pb200_srs_free(h_); }
   CommitKey(const CommitKey&) = delete;
   CommitKey& operator=(const CommitKey&) = delete;
@@ -112,6 +117,13 @@ class CommitKey {
  private:
   pb200_srs_t* h_ = nullptr;
   size_t n_;
+  static std::unique_ptr<CommitKey> from_raw(const uint8_t* bytes, size_t len, int checked) {
+    size_t n = 0;
+    check(pb200_raw_commit_key_points(bytes, len, checked, &n));
+    std::vector<uint8_t> raw(n * 96 + 1);
+    check(pb200_commit_key_from_raw_var_bytes(bytes, len, checked, raw.data()));
+    return std::unique_ptr<CommitKey>(new CommitKey(raw.data(), n));
+  }
 };
 
 // Flat circuit description (what Compiler::preprocess reads out of the Composer, compiler.rs:132-170)
@@ -315,6 +327,14 @@ class Prover {
     check(pb200_prover_new((const uint8_t*)label.data(), label.size(), c.n_constraints, c.selectors[0].data(), c.wires.data(),
                            c.n_witnesses, srs_raw, n_srs_points, &h_));
   }
+  // Prover::try_from_bytes (prover.rs:265-350) for the bytes of Prover::to_bytes; the wiring of the circuit
+  // (4 x constraints witness indices) is not part of that format and comes alongside
+  static std::unique_ptr<Prover> try_from_bytes(const uint8_t* bytes, size_t len, const std::vector<uint32_t>& wires, size_t n_witnesses) {
+    std::unique_ptr<Prover> p(new Prover());
+    p->n_witnesses_ = n_witnesses;
+    check(pb200_prover_from_bytes(bytes, len, wires.data(), n_witnesses, &p->h_));
+    return p;
+  }
   ~Prover() { pb200_prover_free(h_); }
   Prover(const Prover&) = delete;
   Prover& operator=(const Prover&) = delete;
@@ -328,6 +348,7 @@ class Prover {
   }
 
  private:
+  Prover() : n_witnesses_(0) {}
   pb200_prover_t* h_ = nullptr;
   size_t n_witnesses_;
 };

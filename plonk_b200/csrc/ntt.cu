@@ -18,6 +18,8 @@
 //     into the first pass' loads and the last pass' stores.
 //   * Shared-memory layout is split in two 16-byte planes per element so that a warp reading
 //     32 consecutive elements is bank-conflict free.
+#include <cuda.h>  // CUtensorMap (types only: the encoder is looked up through the runtime, no libcuda link)
+
 #include <mutex>
 #include <vector>
 
@@ -58,6 +60,29 @@ PB_D void sts_fr(uint4* s0, uint4* s1, int i, const Fr& r) {
   s1[i] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
 }
 
+// Tile accessors.  Two layouts: PLANES - two 16-byte planes per element (a warp reading 32 consecutive
+// elements is bank-conflict free), filled by ordinary loads; DENSE - elements as they lie in HBM (32 bytes
+// each, rows of T elements), which is what a TMA box writes.
+template <bool DENSE>
+PB_D Fr tile_ld(const uint4* S, int tile, int e) {
+  const uint4 a = DENSE ? S[2 * e] : S[e], b = DENSE ? S[2 * e + 1] : S[tile + e];
+  Fr r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+template <bool DENSE>
+PB_D void tile_st(uint4* S, int tile, int e, const Fr& r) {
+  const uint4 a = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]), b = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+  if (DENSE) {
+    S[2 * e] = a;
+    S[2 * e + 1] = b;
+  } else {
+    S[e] = a;
+    S[tile + e] = b;
+  }
+}
+
 struct PassArgs {
   const uint4* in;
   uint4* out;
@@ -76,12 +101,53 @@ struct PassArgs {
   Fr scalar;
 };
 
-__global__ void __launch_bounds__(kNttThreads) k_ntt_pass(PassArgs a) {
-  extern __shared__ uint4 smem[];
+// K consecutive DIF levels l0 .. l0 + K - 1 of the size-R sub-transforms of a tile, in registers.  At level l
+// the blocks have B = R >> l rows and row j meets row j + B/2 with twiddle w_R^((j mod B/2) << l).  A thread
+// takes the 2^K rows jb + k * s (s = R >> (l0 + K), k < 2^K) of one column: at level l0 + i the partners are
+// 2^(K-1-i) apart in k, and the position of row k inside its half-block is p + (k mod 2^(K-1-i)) * s.
+template <int K, bool DENSE>
+PB_D void ntt_reg_step(uint4* S, const PassArgs& a, int l0, int tid, int tile) {
+  constexpr int E = 1 << K;
+  const int T = 1 << a.log_t;
+  const int log_s = a.r - l0 - K;
+  for (int it = tid; it < (tile >> K); it += kNttThreads) {
+    const int t = it & (T - 1), jj = it >> a.log_t;
+    const int p = jj & ((1 << log_s) - 1), q = jj >> log_s;
+    const int jb = (q << (log_s + K)) + p;
+    Fr v[E];
+#pragma unroll
+    for (int k = 0; k < E; k++) v[k] = tile_ld<DENSE>(S, tile, ((jb + (k << log_s)) << a.log_t) + t);
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+      const int hk = 1 << (K - 1 - i);
+#pragma unroll
+      for (int k = 0; k < E; k++) {
+        if (k & hk) continue;
+        const int pos = p + ((k & (hk - 1)) << log_s);
+        const Fr w = ld_fr(a.w_r, (size_t)pos << (l0 + i));
+        const Fr x = v[k], y = v[k + hk];
+        v[k] = x + y;
+        v[k + hk] = (x - y) * w;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < E; k++) tile_st<DENSE>(S, tile, ((jb + (k << log_s)) << a.log_t) + t, v[k]);
+  }
+}
+
+// TMA = true: the tile of a non-last pass arrives by cp.async.bulk.tensor (3-D tensor map over
+// [batch][rows of lo elements][8 words per element], box = T x 8 words by up to 256 rows) and is signalled
+// on an mbarrier; the twiddle loads of the first register step are in flight meanwhile.  Only for passes
+// whose input is complete and unscaled (no zero padding, no coset pre-scale), see ntt_run.
+// MAXK = 3: the DIF levels run three at a time in registers (full 2048-element tiles: every thread owns 8 rows;
+// 128 registers, 2 CTAs per SM); MAXK = 1: one level at a time (smaller tiles, where an 8-row item list would
+// leave most of the CTA idle; ~56 registers, so more CTAs per SM hide the shared-memory latency).
+template <bool TMA, int MAXK>
+__global__ void __launch_bounds__(kNttThreads, MAXK == 3 ? 2 : 1) k_ntt_pass(PassArgs a, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(128) uint4 smem[];
+  __shared__ __align__(8) unsigned long long tma_bar;
   const int tid = threadIdx.x;
   const int R = 1 << a.r, T = 1 << a.log_t, tile = R << a.log_t;
-  uint4* S0 = smem;
-  uint4* S1 = smem + tile;
   const uint4* in = a.in + 2 * (size_t)blockIdx.y * a.in_stride;
   uint4* out = a.out + 2 * (size_t)blockIdx.y * a.out_stride;
   const size_t blk = blockIdx.x;
@@ -93,6 +159,27 @@ __global__ void __launch_bounds__(kNttThreads) k_ntt_pass(PassArgs a) {
     const size_t h = blk >> log_lo_tiles;
     lo0 = (blk & (((size_t)1 << log_lo_tiles) - 1)) << a.log_t;
     base = (h << (a.r + a.log_lo)) + lo0;
+    if (TMA) {
+      const unsigned bar = (unsigned)__cvta_generic_to_shared(&tma_bar);
+      if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)(tile * 32)) : "memory");
+        const int rows_box = R < 256 ? R : 256;
+        for (int c = 0; c < R; c += rows_box) {
+          const unsigned dst = (unsigned)__cvta_generic_to_shared(smem + 2 * (size_t)c * T);
+          asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                       ::"r"(dst), "l"((unsigned long long)&tmap), "r"(bar), "r"((int)(lo0 * 8)), "r"((int)(h * R + c)), "r"((int)blockIdx.y)
+                       : "memory");
+        }
+      }
+      asm volatile(
+          "{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n\t@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}" ::"r"(bar)
+          : "memory");
+    } else
     for (int idx = tid; idx < tile; idx += kNttThreads) {
       const int j = idx >> a.log_t, t = idx & (T - 1);
       const size_t g = base + ((size_t)j << a.log_lo) + t;
@@ -107,7 +194,7 @@ __global__ void __launch_bounds__(kNttThreads) k_ntt_pass(PassArgs a) {
       } else {
         v = ld_fr_nc(in, g);
       }
-      sts_fr(S0, S1, idx, v);
+      tile_st<TMA>(smem, tile, idx, v);
     }
   } else {
     const int log_k0_tiles = a.log_r0 - a.log_t;
@@ -128,34 +215,39 @@ __global__ void __launch_bounds__(kNttThreads) k_ntt_pass(PassArgs a) {
       } else {
         v = ld_fr_nc(in, g);
       }
-      sts_fr(S0, S1, (j << a.log_t) + t, v);
+      tile_st<TMA>(smem, tile, (j << a.log_t) + t, v);
     }
   }
   __syncthreads();
 
-  // log R radix-2 decimation-in-frequency stages: natural order in, bit-reversed order out.  The last
-  // stage (twiddle 1: a bare add/sub pair) is fused into the store phase below.
-  for (int s = 0; s + 1 < a.r; s++) {
-    const int log_half = a.r - s - 1;
-    const int half = 1 << log_half;
-    for (int b = tid; b < (tile >> 1); b += kNttThreads) {
-      const int t = b & (T - 1);
-      const int jj = b >> a.log_t;
-      const int grp = jj >> log_half, pos = jj & (half - 1);
-      const int j0 = (grp << (log_half + 1)) + pos;
-      const int i0 = (j0 << a.log_t) + t;
-      const int i1 = i0 + (half << a.log_t);
-      const Fr x = lds_fr(S0, S1, i0), y = lds_fr(S0, S1, i1);
-      const Fr w = ld_fr(a.w_r, (size_t)pos << s);
-      sts_fr(S0, S1, i0, x + y);
-      sts_fr(S0, S1, i1, (x - y) * w);
+  // log R decimation-in-frequency levels: natural order in, bit-reversed order out.  The last level
+  // (twiddle 1: a bare add/sub pair) is fused into the store phase below; the others run in groups of up to
+  // three levels held in registers (a thread owns the 8 elements j, j + s, .., j + 7s of one column), so the
+  // tile makes one shared-memory round trip per three levels instead of one per level.
+  {
+    const int m = a.r - 1;
+    int l0 = 0;
+    if (MAXK == 3) {
+      while (m - l0 >= 3) {
+        ntt_reg_step<3, TMA>(smem, a, l0, tid, tile);
+        __syncthreads();
+        l0 += 3;
+      }
+      if (m - l0 == 2) {
+        ntt_reg_step<2, TMA>(smem, a, l0, tid, tile);
+        __syncthreads();
+        l0 += 2;
+      }
     }
-    __syncthreads();
+    for (; l0 < m; l0++) {
+      ntt_reg_step<1, TMA>(smem, a, l0, tid, tile);
+      __syncthreads();
+    }
   }
 
   if (a.r == 0) {  // radix 1: nothing to transform (n = 1, or a degenerate plan)
     for (int idx = tid; idx < tile; idx += kNttThreads) {
-      Fr v = lds_fr(S0, S1, idx);
+      Fr v = tile_ld<TMA>(smem, tile, idx);
       size_t o;
       if (!a.last) {
         o = base + idx;
@@ -175,7 +267,7 @@ __global__ void __launch_bounds__(kNttThreads) k_ntt_pass(PassArgs a) {
   const size_t half_m = a.last ? 0 : ((size_t)1 << (a.r + a.log_lo - 1));
   for (int idx = tid; idx < (tile >> 1); idx += kNttThreads) {
     const int m = idx >> a.log_t, t = idx & (T - 1);
-    const Fr x = lds_fr(S0, S1, ((2 * m) << a.log_t) + t), y = lds_fr(S0, S1, ((2 * m + 1) << a.log_t) + t);
+    const Fr x = tile_ld<TMA>(smem, tile, ((2 * m) << a.log_t) + t), y = tile_ld<TMA>(smem, tile, ((2 * m + 1) << a.log_t) + t);
     const int k0 = (int)(__brev((unsigned)(2 * m)) >> (32 - a.r));
     Fr v[2] = {x + y, x - y};
 #pragma unroll
@@ -354,6 +446,20 @@ static void ntt_plan(int L, int* radices, int* n_pass) {
   }
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point table (no link-time libcuda dependency)
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tmap_encode_fn tmap_encoder() {
+  static tmap_encode_fn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return (tmap_encode_fn)p;
+  }();
+  return fn;
+}
+
 int ntt_run(const uint64_t* d_in, size_t in_len, uint64_t* d_out, uint32_t log_n, int inverse,
             int coset, uint32_t batch, size_t in_stride, size_t out_stride, cudaStream_t st, Arena* ar) {
   if (log_n >= 32) return fail(PB200_ERR_INVALID_DOMAIN, "log_n >= TWO_ADACITY");
@@ -361,8 +467,11 @@ int ntt_run(const uint64_t* d_in, size_t in_len, uint64_t* d_out, uint32_t log_n
   static std::once_flag once;
   static int attr_status = 0;
   std::call_once(once, [] {
-    attr_status = (int)cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (2 << kMaxLogTile) * 16);
+    const int smem_max = (2 << kMaxLogTile) * 16;
+    attr_status = (int)cudaFuncSetAttribute(k_ntt_pass<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (attr_status == 0) attr_status = (int)cudaFuncSetAttribute(k_ntt_pass<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (attr_status == 0) attr_status = (int)cudaFuncSetAttribute(k_ntt_pass<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (attr_status == 0) attr_status = (int)cudaFuncSetAttribute(k_ntt_pass<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (const char* env = getenv("PB200_NTT_PLAN"))
       sscanf(env, "%d,%d,%d", &g_ntt_plan_override[0], &g_ntt_plan_override[1], &g_ntt_plan_override[2]);
   });
@@ -421,7 +530,38 @@ int ntt_run(const uint64_t* d_in, size_t in_len, uint64_t* d_out, uint32_t log_n
     a.scalar = a.has_scalar ? ntt_size_inv((int)log_n) : Fr::zero();
     const size_t tile = (size_t)1 << (a.r + a.log_t);
     dim3 grid((unsigned)(n / tile), batch);
-    PB_LAUNCH(k_ntt_pass, grid, kNttThreads, tile * 32, st, a);
+    // TMA staging of the tile: non-last passes whose input is complete (no zero padding) and unscaled, rows of
+    // at least 128 bytes.  PB200_NTT_TMA=0 keeps the ordinary loads.
+    static const bool tma_env = [] {
+      const char* e = getenv("PB200_NTT_TMA");
+      return !e || atoi(e) != 0;
+    }();
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    bool use_tma = tma_env && !a.last && !a.pre && a.in_len == n && a.log_t >= 2 && a.log_t <= 5 && a.r >= 1 && tmap_encoder() != nullptr;
+    if (use_tma) {
+      const cuuint64_t gdim[3] = {(cuuint64_t)8 << log_lo, (cuuint64_t)(n >> log_lo), (cuuint64_t)batch};
+      const cuuint64_t gstr[2] = {(cuuint64_t)32 << log_lo, (cuuint64_t)a.in_stride * 32};
+      const cuuint32_t rows = (cuuint32_t)std::min<size_t>((size_t)1 << a.r, 256);
+      const cuuint32_t box[3] = {(cuuint32_t)8 << a.log_t, rows, 1};
+      const cuuint32_t estr[3] = {1, 1, 1};
+      const CUresult rc = tmap_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void*)a.in, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (rc != CUDA_SUCCESS) use_tma = false;  // e.g. a stride the descriptor cannot express: ordinary loads
+    }
+    static const int radix_env = [] {  // PB200_NTT_RADIX8=0: one level per shared-memory round trip everywhere
+      const char* e = getenv("PB200_NTT_RADIX8");
+      return e ? atoi(e) : 1;
+    }();
+    const bool k3 = radix_env && tile >= 2048;
+    if (use_tma && k3)
+      PB_LAUNCH((k_ntt_pass<true, 3>), grid, kNttThreads, tile * 32, st, a, tmap);
+    else if (use_tma)
+      PB_LAUNCH((k_ntt_pass<true, 1>), grid, kNttThreads, tile * 32, st, a, tmap);
+    else if (k3)
+      PB_LAUNCH((k_ntt_pass<false, 3>), grid, kNttThreads, tile * 32, st, a, tmap);
+    else
+      PB_LAUNCH((k_ntt_pass<false, 1>), grid, kNttThreads, tile * 32, st, a, tmap);
     PB_CUDA(cudaGetLastError());
     log_h += a.r;
   }
