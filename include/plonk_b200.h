@@ -220,6 +220,12 @@ int pb200_prove_dev(const pb200_prover_t* prover, const uint64_t* d_witnesses, s
 int pb200_profile_enable(int on);
 int pb200_profile_read(double* accumulate_ms, uint64_t* accumulate_adds, uint64_t* accumulate_launches,
                        uint64_t* msm_points);
+/* pb200_profile_read counts the DENSE MSMs (at least a quarter of the window digits non-zero: polynomial
+ * coefficients); sparse ones - the wire-value commitments against the Lagrange-form key, ~1 digit per scalar,
+ * mostly the over-long-bucket kernels - are accumulated separately so that they do not blur the dominant
+ * kernel's rate. */
+int pb200_profile_read_sparse(double* accumulate_ms, uint64_t* accumulate_adds, uint64_t* accumulate_launches,
+                              uint64_t* msm_points);
 /* Lagrange form of a commit key: out[j] = [L_j(x)]G = (1/n) sum_i w^(-ij) points[i] for the first
    n = 2^k points of CommitKey::powers_of_g (reference src/commitment_scheme/kzg10/key.rs:36-41), by an
    inverse NTT over group elements on the device.  Host buffers, n affine points of 96 bytes each (the

@@ -107,6 +107,7 @@ int g1_check_raw(const uint8_t* raw, size_t n);
 int raw_commit_key_parse(const uint8_t* bytes, size_t len, int checked, size_t* n_points, uint8_t* out_raw);
 extern std::atomic<int> g_prof_on;
 extern std::atomic<uint64_t> g_prof_acc_ns, g_prof_acc_adds, g_prof_acc_launches, g_prof_acc_points;
+extern std::atomic<uint64_t> g_prof_sp_ns, g_prof_sp_adds, g_prof_sp_launches, g_prof_sp_points;
 void srs_free(pb200_srs* s);
 }  // namespace pb
 
@@ -370,6 +371,7 @@ int pb200_srs_setup_from_secret(const uint64_t* x, const uint64_t* g_scalar, siz
 
 int pb200_profile_enable(int on) {
   g_prof_acc_ns = 0; g_prof_acc_adds = 0; g_prof_acc_launches = 0; g_prof_acc_points = 0;
+  g_prof_sp_ns = 0; g_prof_sp_adds = 0; g_prof_sp_launches = 0; g_prof_sp_points = 0;
   g_prof_on = on ? 1 : 0;
   return 0;
 }
@@ -378,6 +380,14 @@ int pb200_profile_read(double* accumulate_ms, uint64_t* accumulate_adds, uint64_
   if (accumulate_adds) *accumulate_adds = g_prof_acc_adds.load();
   if (accumulate_launches) *accumulate_launches = g_prof_acc_launches.load();
   if (msm_points) *msm_points = g_prof_acc_points.load();
+  return 0;
+}
+
+int pb200_profile_read_sparse(double* accumulate_ms, uint64_t* accumulate_adds, uint64_t* accumulate_launches, uint64_t* msm_points) {
+  if (accumulate_ms) *accumulate_ms = (double)g_prof_sp_ns.load() * 1e-6;
+  if (accumulate_adds) *accumulate_adds = g_prof_sp_adds.load();
+  if (accumulate_launches) *accumulate_launches = g_prof_sp_launches.load();
+  if (msm_points) *msm_points = g_prof_sp_points.load();
   return 0;
 }
 

@@ -695,28 +695,32 @@ struct AffRound {
   const unsigned* offsets; // [batch][nb + 1]
   const unsigned* max_len; // [batch] longest bucket
   uint4* prefix;           // [batch][pair slots] running products (48 B each)
-  uint2* desc;             // [batch][pair slots] (first input position, output slot)
+  uint4* desc;             // [batch][pair slots] (first operand, second operand, output slot, -)
   uint4* sums;             // [batch][nb] affine bucket sums
+  uint4* factor;           // [batch][threads] product of the other threads of the CTA (48 B)
+  uint4* ctot;             // [batch][ctas_max] CTA totals, inverted in place between the two kernels
+  unsigned* npairs;        // [batch][threads]
   unsigned nb;
   size_t cap, in_cap, out_cap, slots;  // slots = threads per batch entry * kAffK / 2
   unsigned threads;                    // threads per batch entry in this round
+  unsigned ctas_max;                   // stride of ctot
   int r;
 };
 
+// Operand addressing.  Round 0: an operand is a (table index << 1 | sign) reference; later rounds: a position
+// in the input layout.
 template <bool FIRST>
-PB_D G1Affine aff_load(const AffRound& a, unsigned b, unsigned pos) {
-  if (FIRST) {
-    const unsigned e = __ldg(a.sorted + (size_t)b * a.cap + pos);
-    G1Affine p = ld_affine(a.table, e >> 1);
-    if ((e & 1u) && !p.is_inf()) p.y = p.y.neg();
-    return p;
-  } else {
-    const uint4* q = a.in + 6 * ((size_t)b * a.in_cap + pos);
-    G1Affine p;
-    p.x = ld_fp(q);
-    p.y = ld_fp(q + 3);
-    return p;
-  }
+PB_D const uint4* aff_src(const AffRound& a, unsigned b, unsigned ref) {
+  return FIRST ? a.table + 6 * (size_t)(ref >> 1) : a.in + 6 * ((size_t)b * a.in_cap + ref);
+}
+template <bool FIRST>
+PB_D G1Affine aff_load(const AffRound& a, unsigned b, unsigned ref) {
+  const uint4* q = aff_src<FIRST>(a, b, ref);
+  G1Affine p;
+  p.x = ld_fp(q);
+  p.y = ld_fp(q + 3);
+  if (FIRST && (ref & 1u) && !p.is_inf()) p.y = p.y.neg();
+  return p;
 }
 PB_D void aff_store(const AffRound& a, unsigned b, unsigned slot, const G1Affine& p) {
   if (slot & 0x80000000u)
@@ -724,11 +728,20 @@ PB_D void aff_store(const AffRound& a, unsigned b, unsigned slot, const G1Affine
   else
     st_affine(a.out, (size_t)b * a.out_cap + slot, p);
 }
+PB_D void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
 
+// A round is three launches, so that no multiply-pipe time is spent waiting for an inversion:
+//   k_msm_affine_fwd   phases A1 + A2 and the CTA's product tree: every thread leaves its pair list, the running
+//                      products, its pair count and the factor F_t = (product of all OTHER threads of the CTA);
+//                      the CTA leaves its total T_c.
+//   k_fp_batch_inverse all T_c of the round (a few hundred) inverted together: one CTA per batch entry, serial
+//                      Montgomery chains + warp scans + ONE binary-GCD inversion.
+//   k_msm_affine_back  1 / (thread product) = (1 / T_c) * F_t, then phase C.
 template <bool FIRST>
-__global__ void __launch_bounds__(kAffThreads) k_msm_affine_round(AffRound a) {
+__global__ void __launch_bounds__(kAffThreads, 4) k_msm_affine_fwd(AffRound a) {
   __shared__ uint4 sh_tot[4][3];
-  __shared__ uint4 sh_inv[4][3];
   const unsigned b = blockIdx.y;
   const int r = a.r;
   if (r > 0 && (1u << r) >= a.max_len[b]) return;  // every bucket is finished (uniform per CTA)
@@ -738,8 +751,8 @@ __global__ void __launch_bounds__(kAffThreads) k_msm_affine_round(AffRound a) {
   const unsigned total = aff_off(off[nb], nb, r);  // end of layout r
   const unsigned pos0 = t * kAffK, pos1 = min(total, pos0 + kAffK);
   const size_t slot0 = (size_t)b * a.slots + t;  // pair i of this thread lives at slot0 + i * threads
-  Fp run = Fp::one();
   int np = 0;
+  // ---- phase A1: list this thread's pairs (no point is touched yet); move the odd elements on ----
   if (pos0 < total) {
     // first bucket whose range reaches past pos0: the largest bk with off_r[bk] <= pos0
     unsigned lo = 0, hi = nb;  // off_r[0] = 0 <= pos0
@@ -747,6 +760,7 @@ __global__ void __launch_bounds__(kAffThreads) k_msm_affine_round(AffRound a) {
       const unsigned mid = (lo + hi) >> 1;
       if (aff_off(off[mid], mid, r) <= pos0) lo = mid; else hi = mid;
     }
+    const unsigned* refs = a.sorted + (size_t)b * a.cap;
     for (unsigned bk = lo; bk < nb; bk++) {
       const unsigned o = aff_off(off[bk], bk, r);
       if (o >= pos1) break;
@@ -754,26 +768,50 @@ __global__ void __launch_bounds__(kAffThreads) k_msm_affine_round(AffRound a) {
       const unsigned L = aff_len(L0, r);
       if (L == 0) continue;
       if (L == 1) {
-        if (FIRST && o >= pos0) aff_store(a, b, 0x80000000u | bk, aff_load<FIRST>(a, b, o));  // single entry: the bucket sum
+        if (FIRST && o >= pos0) aff_store(a, b, 0x80000000u | bk, aff_load<FIRST>(a, b, __ldg(refs + o)));  // single entry: the bucket sum
         continue;
       }
       const unsigned o_next = aff_off(off[bk], bk, r + 1);
       unsigned e = o >= pos0 ? 0u : ((pos0 - o + 1u) & ~1u);  // first even element at or after pos0
       for (; e + 1 < L && o + e < pos1; e += 2) {
-        const G1Affine p1 = aff_load<FIRST>(a, b, o + e), p2 = aff_load<FIRST>(a, b, o + e + 1);
-        Fp d = Fp::one();
-        aff_classify(p1, p2, &d);
-        const size_t s = slot0 + (size_t)np * a.threads;
-        st_fp(a.prefix + 3 * s, run);
-        a.desc[s] = make_uint2(o + e, L == 2 ? (0x80000000u | bk) : (o_next + (e >> 1)));
-        run = run * d;
+        const unsigned r1 = FIRST ? __ldg(refs + o + e) : o + e, r2 = FIRST ? __ldg(refs + o + e + 1) : o + e + 1;
+        a.desc[slot0 + (size_t)np * a.threads] = make_uint4(r1, r2, L == 2 ? (0x80000000u | bk) : (o_next + (e >> 1)), 0u);
         np++;
       }
       if ((L & 1u) && o + L - 1 >= pos0 && o + L - 1 < pos1)  // odd element out: moves on unchanged
-        aff_store(a, b, o_next + ((L - 1) >> 1), aff_load<FIRST>(a, b, o + L - 1));
+        aff_store(a, b, o_next + ((L - 1) >> 1), aff_load<FIRST>(a, b, FIRST ? __ldg(refs + o + L - 1) : o + L - 1));
     }
   }
-  // ---- phase B: invert the 128 thread totals together ----
+  a.npairs[(size_t)b * a.threads + t] = (unsigned)np;
+  // ---- phase A2: running product of the divisors; the x coordinates of the next pair are in flight ----
+  Fp run = Fp::one();
+  {
+    Fp nx1 = Fp::zero(), nx2 = Fp::zero();
+    uint4 nds = make_uint4(0, 0, 0, 0);
+    if (np > 0) {
+      nds = a.desc[slot0];
+      nx1 = ld_fp(aff_src<FIRST>(a, b, nds.x));
+      nx2 = ld_fp(aff_src<FIRST>(a, b, nds.y));
+    }
+#pragma unroll 1
+    for (int i = 0; i < np; i++) {
+      const Fp x1 = nx1, x2 = nx2;
+      const uint4 ds = nds;
+      if (i + 1 < np) {
+        nds = a.desc[slot0 + (size_t)(i + 1) * a.threads];
+        nx1 = ld_fp(aff_src<FIRST>(a, b, nds.x));
+        nx2 = ld_fp(aff_src<FIRST>(a, b, nds.y));
+      }
+      Fp d = x2 - x1;
+      if (d.is_zero() || x1.is_zero() || x2.is_zero()) {  // rare: equal abscissae or a possible identity - look at the whole points
+        d = Fp::one();
+        aff_classify(aff_load<FIRST>(a, b, ds.x), aff_load<FIRST>(a, b, ds.y), &d);
+      }
+      st_fp(a.prefix + 3 * (slot0 + (size_t)i * a.threads), run);
+      run = run * d;
+    }
+  }
+  // ---- the CTA's product tree: F_t = product of the other 127 thread products, T_c = product of all ----
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   Fp incl = run, sfx = run;
 #pragma unroll 1
@@ -787,29 +825,109 @@ __global__ void __launch_bounds__(kAffThreads) k_msm_affine_round(AffRound a) {
   if (lane == 31) after = Fp::one();
   if (lane == 31) st_fp(sh_tot[warp], incl);
   __syncthreads();
+  Fp others = Fp::one();  // the other three warps
+#pragma unroll
+  for (int w = 0; w < 4; w++)
+    if (w != warp) others = others * ld_fp(sh_tot[w]);
+  st_fp(a.factor + 3 * ((size_t)b * a.threads + t), (before * after) * others);
+  if (threadIdx.x == 0) st_fp(a.ctot + 3 * ((size_t)b * a.ctas_max + blockIdx.x), others * ld_fp(sh_tot[0]));
+}
+
+// In-place inverses of n Fp values per batch entry (none of them zero), one CTA of 256 threads per batch entry.
+__global__ void __launch_bounds__(256) k_fp_batch_inverse(uint4* vals, uint4* scratch, unsigned n, size_t stride, const unsigned* max_len, int r) {
+  __shared__ uint4 sh_tot[8][3];
+  __shared__ uint4 sh_inv[8][3];
+  const unsigned b = blockIdx.x;
+  if (r > 0 && (1u << r) >= max_len[b]) return;
+  uint4* v = vals + 3 * (size_t)b * stride;
+  uint4* pre = scratch + 3 * (size_t)b * stride;
+  const unsigned m = (n + 255u) / 256u, lo = min(n, threadIdx.x * m), hi = min(n, lo + m);
+  Fp run = Fp::one();
+  for (unsigned i = lo; i < hi; i++) {
+    st_fp(pre + 3 * i, run);
+    run = run * ld_fp(v + 3 * i);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Fp incl = run, sfx = run;
+#pragma unroll 1
+  for (int d = 1; d < 32; d <<= 1) {
+    const Fp up = shfl_up_fp(incl, d), dn = shfl_down_fp(sfx, d);
+    if (lane >= d) incl = incl * up;
+    if (lane + d < 32) sfx = sfx * dn;
+  }
+  Fp before = shfl_up_fp(incl, 1), after = shfl_down_fp(sfx, 1);
+  if (lane == 0) before = Fp::one();
+  if (lane == 31) after = Fp::one();
+  if (lane == 31) st_fp(sh_tot[warp], incl);
+  __syncthreads();
   if (threadIdx.x == 0) {
-    const Fp w0 = ld_fp(sh_tot[0]), w1 = ld_fp(sh_tot[1]), w2 = ld_fp(sh_tot[2]), w3 = ld_fp(sh_tot[3]);
-    const Fp w01 = w0 * w1, w23 = w2 * w3;
-    const Fp inv = fp_inv_bingcd(w01 * w23);
-    const Fp i01 = inv * w23, i23 = inv * w01;  // 1/(w0 w1), 1/(w2 w3)
-    st_fp(sh_inv[0], i01 * w1);
-    st_fp(sh_inv[1], i01 * w0);
-    st_fp(sh_inv[2], i23 * w3);
-    st_fp(sh_inv[3], i23 * w2);
+    Fp w[8], pf[8];
+    Fp acc = Fp::one();
+    for (int k = 0; k < 8; k++) {
+      w[k] = ld_fp(sh_tot[k]);
+      pf[k] = acc;
+      acc = acc * w[k];
+    }
+    Fp inv = fp_inv_bingcd(acc);
+    for (int k = 7; k >= 0; k--) {
+      st_fp(sh_inv[k], inv * pf[k]);  // 1 / w[k]
+      inv = inv * w[k];
+    }
   }
   __syncthreads();
   Fp inv_run = ld_fp(sh_inv[warp]) * (before * after);  // 1 / (this thread's product)
-  // ---- phase C: walk back, finish the additions ----
+  for (unsigned i = hi; i-- > lo;) {
+    const Fp x = ld_fp(v + 3 * i);
+    st_fp(v + 3 * i, inv_run * ld_fp(pre + 3 * i));
+    inv_run = inv_run * x;
+  }
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(kAffThreads, 4) k_msm_affine_back(AffRound a) {
+  extern __shared__ __align__(16) uint4 sh_stage[];  // [kAffThreads][15]: the next pair's operands and running product
+  const unsigned b = blockIdx.y;
+  if (a.r > 0 && (1u << a.r) >= a.max_len[b]) return;
+  const unsigned t = blockIdx.x * kAffThreads + threadIdx.x;
+  const size_t slot0 = (size_t)b * a.slots + t;
+  const int np = (int)a.npairs[(size_t)b * a.threads + t];
+  if (np == 0) return;
+  uint4* stage = sh_stage + 15 * threadIdx.x;
+  auto fetch = [&](int i) {
+    const size_t s = slot0 + (size_t)i * a.threads;
+    const uint4 ds = a.desc[s];
+    const uint4 *q1 = aff_src<FIRST>(a, b, ds.x), *q2 = aff_src<FIRST>(a, b, ds.y), *q3 = a.prefix + 3 * s;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      cp_async16(stage + k, q1 + k);
+      cp_async16(stage + 6 + k, q2 + k);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) cp_async16(stage + 12 + k, q3 + k);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  fetch(np - 1);
+  // 1 / (this thread's product) = (1 / T_c) * F_t
+  Fp inv_run = ld_fp(a.ctot + 3 * ((size_t)b * a.ctas_max + blockIdx.x)) * ld_fp(a.factor + 3 * ((size_t)b * a.threads + t));
+  // ---- phase C: walk back, finish the additions; pair i - 1 is fetched while pair i is computed ----
 #pragma unroll 1
   for (int i = np - 1; i >= 0; i--) {
-    const size_t s = slot0 + (size_t)i * a.threads;
-    const uint2 ds = a.desc[s];
-    const G1Affine p1 = aff_load<FIRST>(a, b, ds.x), p2 = aff_load<FIRST>(a, b, ds.x + 1);
+    const uint4 ds = a.desc[slot0 + (size_t)i * a.threads];
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    G1Affine p1, p2;
+    p1.x = ld_fp(stage); p1.y = ld_fp(stage + 3);
+    p2.x = ld_fp(stage + 6); p2.y = ld_fp(stage + 9);
+    const Fp pre = ld_fp(stage + 12);
+    if (i > 0) fetch(i - 1);  // the slot has been read: reuse it
+    if (FIRST) {
+      if ((ds.x & 1u) && !p1.is_inf()) p1.y = p1.y.neg();
+      if ((ds.y & 1u) && !p2.is_inf()) p2.y = p2.y.neg();
+    }
     Fp d = Fp::one();
     const int kind = aff_classify(p1, p2, &d);
-    const Fp inv_d = inv_run * ld_fp(a.prefix + 3 * s);
+    const Fp inv_d = inv_run * pre;
     inv_run = inv_run * d;
-    aff_store(a, b, ds.y, aff_finish(kind, p1, p2, inv_d));
+    aff_store(a, b, ds.z, aff_finish(kind, p1, p2, inv_d));
   }
 }
 
@@ -990,6 +1108,8 @@ __global__ void __launch_bounds__(256) k_fp_product_peak(uint4* out, int iters, 
 // launching stream; read by bench.py for the roofline line.
 std::atomic<int> g_prof_on{0};
 std::atomic<uint64_t> g_prof_acc_ns{0}, g_prof_acc_adds{0}, g_prof_acc_launches{0}, g_prof_acc_points{0};
+// the same for sparse MSMs (fewer than a quarter of the window digits non-zero: the wire-value commitments)
+std::atomic<uint64_t> g_prof_sp_ns{0}, g_prof_sp_adds{0}, g_prof_sp_launches{0}, g_prof_sp_points{0};
 
 static int pick_window(size_t n_points) {
   if (const char* env = getenv("PB200_MSM_C")) {
@@ -1022,6 +1142,15 @@ struct MsmTail {
   uint32_t batch = 0;
   size_t words_per_entry() const { return (size_t)(plan.ndig + 1) * 48; }  // 32-bit words of one batch entry
 };
+
+// PB200_MSM_AFFINE=1: bucket accumulation by batched affine additions (k_msm_affine_round) instead of XYZZ
+static bool msm_affine_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("PB200_MSM_AFFINE");
+    return e && atoi(e) != 0;
+  }();
+  return on;
+}
 
 // pair slots (running product + descriptor) per batch entry: the widest round's thread count x kAffK / 2
 static size_t aff_slots(size_t cap, size_t nb) {
@@ -1104,10 +1233,7 @@ static int msm_enqueue(const pb200_srs* srs, size_t first, const uint64_t* d_sca
   PB_ALLOC(scope, counts, (size_t)batch * nb * 4);
   PB_ALLOC(scope, offsets, (size_t)batch * (nb + 1) * 4);
   PB_ALLOC(scope, order, (size_t)batch * nb * 4);
-  static const bool affine = [] {
-    const char* e = getenv("PB200_MSM_AFFINE");
-    return e && atoi(e) != 0;
-  }();
+  const bool affine = msm_affine_enabled();
   unsigned *n_heavy = nullptr, *heavy_pre = nullptr, *max_len = nullptr;
   PB_ALLOC(scope, max_len, (size_t)batch * 4);
   PB_ALLOC(scope, n_heavy, (size_t)batch * 4);
@@ -1143,16 +1269,24 @@ static int msm_enqueue(const pb200_srs* srs, size_t first, const uint64_t* d_sca
     // input positions of round r: layout 0 is exact, layout r >= 1 has at most one slot of slack per bucket
     auto positions = [&](int r) { return r == 0 ? cap : (cap >> r) + nb + 1; };
     const size_t slots = aff_slots(cap, nb);
-    uint4 *bufA = nullptr, *bufB = nullptr, *pre = nullptr;
-    uint2* desc = nullptr;
+    uint4 *bufA = nullptr, *bufB = nullptr, *pre = nullptr, *factor = nullptr, *ctot = nullptr, *cpre = nullptr;
+    uint4* desc = nullptr;
+    unsigned* npairs = nullptr;
+    const size_t threads_max = slots / (kAffK / 2);
+    const unsigned ctas_max = (unsigned)(threads_max / kAffThreads);
     PB_ALLOC(scope, bufA, (size_t)batch * capA * 96);
     PB_ALLOC(scope, bufB, (size_t)batch * capB * 96);
     PB_ALLOC(scope, pre, (size_t)batch * slots * 48);
-    PB_ALLOC(scope, desc, (size_t)batch * slots * 8);
+    PB_ALLOC(scope, desc, (size_t)batch * slots * 16);
+    PB_ALLOC(scope, factor, (size_t)batch * threads_max * 48);
+    PB_ALLOC(scope, npairs, (size_t)batch * threads_max * 4);
+    PB_ALLOC(scope, ctot, (size_t)batch * ctas_max * 48);
+    PB_ALLOC(scope, cpre, (size_t)batch * ctas_max * 48);
     PB_CUDA(cudaMemsetAsync(sums, 0, (size_t)batch * nb * 96, st));
     for (int r = 0; r < rounds; r++) {
       AffRound a;
       a.table = srs->table; a.sorted = sorted; a.offsets = offsets; a.max_len = max_len; a.prefix = pre; a.desc = desc; a.sums = sums;
+      a.factor = factor; a.ctot = ctot; a.npairs = npairs; a.ctas_max = ctas_max;
       a.nb = nb; a.cap = cap; a.r = r;
       a.in = (r & 1) ? bufA : bufB;   // layout r: odd layouts live in A, even ones (>= 2) in B
       a.out = (r & 1) ? bufB : bufA;  // layout r + 1
@@ -1161,10 +1295,16 @@ static int msm_enqueue(const pb200_srs* srs, size_t first, const uint64_t* d_sca
       const unsigned ctas = div_up(div_up(positions(r), kAffK), kAffThreads);
       a.threads = ctas * kAffThreads;
       a.slots = slots;
+      const size_t stage_bytes = (size_t)kAffThreads * 15 * 16;  // one 240-byte staging slot per thread
       if (r == 0)
-        PB_LAUNCH(k_msm_affine_round<true>, dim3(ctas, batch), kAffThreads, 0, st, a);
+        PB_LAUNCH(k_msm_affine_fwd<true>, dim3(ctas, batch), kAffThreads, 0, st, a);
       else
-        PB_LAUNCH(k_msm_affine_round<false>, dim3(ctas, batch), kAffThreads, 0, st, a);
+        PB_LAUNCH(k_msm_affine_fwd<false>, dim3(ctas, batch), kAffThreads, 0, st, a);
+      PB_LAUNCH(k_fp_batch_inverse, batch, 256, 0, st, ctot, cpre, ctas, (size_t)ctas_max, (const unsigned*)max_len, r);
+      if (r == 0)
+        PB_LAUNCH(k_msm_affine_back<true>, dim3(ctas, batch), kAffThreads, stage_bytes, st, a);
+      else
+        PB_LAUNCH(k_msm_affine_back<false>, dim3(ctas, batch), kAffThreads, stage_bytes, st, a);
     }
     if (prof_ev) PB_CUDA(cudaEventRecord(prof_ev[1], st));
     if (d_totals) *d_totals = offsets + nb;
@@ -1304,10 +1444,11 @@ int msm_run(const pb200_srs* srs, size_t first, const uint64_t* d_scalars, size_
     if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) {
       uint64_t adds = 0;
       for (unsigned t : h_tot) adds += t;
-      g_prof_acc_ns.fetch_add((uint64_t)(ms * 1e6));
-      g_prof_acc_adds.fetch_add(adds);
-      g_prof_acc_points.fetch_add((uint64_t)n * batch);
-      g_prof_acc_launches.fetch_add(1);
+      const bool sparse = adds * 4 < (uint64_t)n * batch * srs->W;
+      (sparse ? g_prof_sp_ns : g_prof_acc_ns).fetch_add((uint64_t)(ms * 1e6));
+      (sparse ? g_prof_sp_adds : g_prof_acc_adds).fetch_add(adds);
+      (sparse ? g_prof_sp_points : g_prof_acc_points).fetch_add((uint64_t)n * batch);
+      (sparse ? g_prof_sp_launches : g_prof_acc_launches).fetch_add(1);
     }
   }
   scope.release();  // the stream was synchronised above: the scratch is dead
@@ -1406,9 +1547,10 @@ size_t msm_workspace_bytes(const pb200_srs* srs, size_t n, uint32_t batch) {
   b += 2 * ((size_t)batch * n_groups * 192 + 256);     // S, A
   b += (size_t)batch * (8 * 16 + n_groups / 256 + 2) * (n_groups / (16 * kClassChunk) + 2) * 192 + 256;  // classes x chunks
   b += (size_t)batch * 9 * 192 + 256;                  // result
-  {  // batched-affine rounds: two point buffers, running products, pair descriptors
+  if (msm_affine_enabled()) {  // batched-affine rounds: two point buffers, running products, pair descriptors
     b += (size_t)batch * ((cap / 2 + nb + 2) + (cap / 4 + nb + 2)) * 96 + 512;
-    b += (size_t)batch * aff_slots(cap, nb) * (48 + 8) + 512;
+    b += (size_t)batch * aff_slots(cap, nb) * (48 + 16) + 512;
+    b += (size_t)batch * (aff_slots(cap, nb) / (kAffK / 2)) * (48 + 4 + 1) + 2048;  // factor, npairs, CTA totals
   }
   return b + 4096;
 }
