@@ -281,7 +281,7 @@ def run_ours(args):
     ntt = ntt_microbench(L, torch, imad.value)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(arrays, 2)
+        cpu = cpu_baseline(2)
     extra = {}
     if ms_synth is not None:
         host_threads = len(os.sched_getaffinity(0))
@@ -494,20 +494,8 @@ def ntt_microbench(L, torch, imad_peak):
     return out
 
 
-def cpu_baseline(arrays, n_proofs):
-    """Restated reference (oracle/cref.cpp, all host threads) on a bounded sample of the same workload."""
-    from oracle import cref
-
-    threads = cref.best_threads()
-    srs = cref.srs_from_secret(SRS_POINTS, SRS_X, SRS_G, threads)
-    ca = arrays
-    prover = cref.CrefProver(LABEL, ca, srs, threads)
-    prover.prove(blinders_for(99), ca)  # warm-up: thread pool, first-touch pages
-    t0 = time.time()
-    for i in range(n_proofs):
-        prover.prove(blinders_for(i), ca)
-    dt = time.time() - t0
-    # the two kernels on their own, same sizes as the GPU microbenchmarks (SURVEY.md section 8d)
+def cpu_kernel_rates(cref, srs, threads):
+    """The two kernels on their own on the CPU, same sizes as the GPU microbenchmarks."""
     import random
 
     rng = random.Random(19)
@@ -522,13 +510,19 @@ def cpu_baseline(arrays, n_proofs):
     cref.msm(srs, scalars, threads)
     msm_s = time.time() - t0
     window = int(math.log(SRS_POINTS)) + 2  # msm_variable_base's window rule
-    return {"value": n_proofs / dt, "unit": "proofs/s", "cores": threads, "kind": "port",
-            "sample": f"{n_proofs} proof(s) after one warm-up proof of the same 2^16-gate circuit, C++/OpenMP restatement of the reference prover "
-                      f"(the Rust crate cannot be built here: no cargo/rustc); "
-                      f"{cref.thread_policy()}",
-            "coset_ntt_2^19": {"ms": ntt_s * 1e3, "butterflies_per_s": (n19 // 2) * (LOG_GATES + 3) / ntt_s},
+    return {"coset_ntt_2^19": {"ms": ntt_s * 1e3, "butterflies_per_s": (n19 // 2) * (LOG_GATES + 3) / ntt_s},
             "msm_2^16": {"ms": msm_s * 1e3, "points_per_s": SRS_POINTS / msm_s,
                          "bucket_adds_per_s": SRS_POINTS * math.ceil(255 / window) / msm_s, "window_bits": window}}
+
+
+def cpu_baseline(n_proofs):
+    """Restated reference (oracle/cref.cpp) on a bounded sample of the same workload.  It runs as the reference arm
+    itself - `bench.py --impl reference` in a child process - so that the number is the one the arm reports: inside
+    this process, next to torch's OpenMP runtime and the proving threads, the same code measured 2.3 x slower."""
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(n_proofs), "--warmup", "1", "--cpu-kernels"],
+                         capture_output=True, text=True, timeout=900, env={k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "RANK", "WORLD_SIZE", "LOCAL_RANK")})
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    return line["cpu_baseline"]
 
 
 def run_reference(args):
@@ -561,14 +555,17 @@ def run_reference(args):
         prover.prove(blinders_for(1000 + i), arrays)
     dt = time.time() - t0
     value = args.steps / dt
-    sample = (f"each step = 1 proof of the 2^16-gate workload; {cref.thread_policy()}; C++/OpenMP restatement "
-              "(the Rust reference cannot be built here)")
+    sample = (f"each step = 1 proof of the 2^16-gate workload ({args.steps} timed after {args.warmup} warm-up); {cref.thread_policy()}; "
+              "C++/OpenMP restatement (the Rust reference cannot be built here)")
+    cpu = {"value": value, "unit": "proofs/s", "cores": threads, "kind": "port", "sample": sample}
+    if args.cpu_kernels:
+        cpu.update(cpu_kernel_rates(cref, srs, threads))
     print(json.dumps({
         "impl": "reference", "metric": "proofs/sec @ 2^16 gates", "value": value, "unit": "proofs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (CPU)", "data": "synthetic",
         "config": {"workload": workload, "proofs_per_step": 1},
-        "cpu_baseline": {"value": value, "unit": "proofs/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -581,6 +578,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--inflight", type=int, default=int(os.environ.get("PB200_INFLIGHT", "12")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-kernels", action="store_true", help="(reference arm) also time one coset NTT 2^19 and one MSM 2^16 on the CPU")
     ap.add_argument("--no-msm-sweep", action="store_true", help="skip extra.msm_sweep (BASELINE.json configs[3])")
     ap.add_argument("--msm-sizes", default="16,18,20,22,24", help="log2 point counts of the sharded-MSM sweep")
     ap.add_argument("--msm-iters", type=int, default=3)
