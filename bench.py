@@ -90,6 +90,34 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def host_cpu_state():
+    """CPU bandwidth state of this container (cgroup v2 cpu.max / cpu.stat, v1 fallbacks): quota in CPUs and the
+    cumulative throttling counters - proving is host-driven (one thread per proof in flight), so a throttled
+    container shows up as lost proofs/s, not as a slow GPU."""
+    st = {"quota_cpus": None, "nr_throttled": None, "throttled_usec": None, "usable_cpus": len(os.sched_getaffinity(0))}
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        st["quota_cpus"] = None if q == "max" else int(q) / int(per)
+        for ln in open("/sys/fs/cgroup/cpu.stat"):
+            k, v = ln.split()
+            if k in ("nr_throttled", "throttled_usec"):
+                st[k] = int(v)
+    except (OSError, ValueError):
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            st["quota_cpus"] = q / per if q > 0 else None
+            for ln in open("/sys/fs/cgroup/cpu/cpu.stat"):
+                k, v = ln.split()
+                if k == "nr_throttled":
+                    st[k] = int(v)
+                if k == "throttled_time":
+                    st["throttled_usec"] = int(v) // 1000
+        except (OSError, ValueError):
+            pass
+    return st
+
+
 def finish_dist(world):
     if world > 1:
         import torch.distributed as dist
@@ -202,11 +230,20 @@ def run_ours(args):
     run_steps(args.warmup, True)
     run_steps(max(1, args.warmup // 2), False)
     sampler = ClockSampler(local)
-    sampler.start()
+    use_sampler = rank == 0 and not os.environ.get("PB200_NO_SAMPLER")  # one nvidia-smi poller per box is enough
+    if use_sampler:
+        sampler.start()
+    host = {"before": host_cpu_state()}
     launches0 = L.pb200_launch_count()
+    cpu0 = time.process_time()
     ms_res = timed(args.steps, True)
+    host["cpu_s_value"] = time.process_time() - cpu0
+    host["after_value"] = host_cpu_state()
     launches = L.pb200_launch_count() - launches0
+    cpu0 = time.process_time()
     ms_e2e = timed(args.steps, False)
+    host["cpu_s_e2e"] = time.process_time() - cpu0
+    host["after_e2e"] = host_cpu_state()
     ms_synth = None
     if args.circuit == "bench":
         run_steps(1, "synth")
@@ -229,7 +266,9 @@ def run_ours(args):
     check(L.pb200_profile_read_sparse(ctypes.byref(sp_ms), ctypes.byref(sp_adds), ctypes.byref(sp_launches), ctypes.byref(sp_points)))
     check(L.pb200_profile_enable(0))
     sampler.stop_flag = True
-    sampler.join()
+    if use_sampler:
+        sampler.join()
+    host["after_synthesis"] = host_cpu_state()
 
     total_proofs = args.steps * inflight * world
     value = total_proofs / (ms_res * 1e-3)
@@ -282,7 +321,7 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(2)
-    extra = {}
+    extra = {"host": host}
     if ms_synth is not None:
         host_threads = len(os.sched_getaffinity(0))
         extra["e2e_with_synthesis"] = {
