@@ -525,8 +525,8 @@ __global__ void __launch_bounds__(128) k_msm_heavy_combine(const uint4* partials
 }
 
 // ---------------------------------------------------------------------------------------------
-// Bucket accumulation by batched affine additions (the default since round 2; PB200_MSM_AFFINE=0 selects
-// the XYZZ kernels above).
+// Bucket accumulation by batched affine additions (opt-in: PB200_MSM_AFFINE=1; the XYZZ kernels above are the
+// default because they measure faster - 194-196 against 188.6 proofs/s - see DESIGN.md section 4).
 //
 // An affine addition needs lambda = (y2 - y1) / (x2 - x1): 2M + 1S once 1 / (x2 - x1) is known, against
 // 8M + 2S for the inversion-free XYZZ mixed addition.  Inversions are shared with Montgomery's trick
@@ -542,13 +542,15 @@ __global__ void __launch_bounds__(128) k_msm_heavy_combine(const uint4* partials
 //   * Work split.  A thread owns kAffK consecutive input POSITIONS of the round's layout, whatever buckets
 //     they belong to (binary search for the first one), i.e. up to kAffK/2 pairs: a 30 000-entry bucket and
 //     30 000 single-pair buckets are the same work list.  No bucket ordering, no heavy-bucket path.
-//   * Inversions.  Phase A: the thread walks its pairs, d_i = x2 - x1 (2 y1 for a doubling, 1 when a pair
-//     needs no division: an identity operand or P + (-P)), stores the running product before d_i in
-//     scratch.  Phase B: the CTA's 128 thread totals are inverted together - warp prefix/suffix products by
-//     shuffles, ONE inversion per CTA by lane 0 with a binary extended GCD on the integer-add pipe (the
-//     multiply pipe is the bottleneck of these kernels and stays free for the other warps and CTAs).
-//     Phase C: the thread walks back, 1/d_i = (running inverse) x (stored prefix), and finishes each
-//     addition: 5M + 1S + ~0.4M of sharing per addition, 32 % fewer multiply instructions than XYZZ.
+//   * A round is three launches.  k_msm_affine_fwd: the thread lists its pairs, then walks them with
+//     d_i = x2 - x1 (2 y1 for a doubling, 1 when a pair needs no division: an identity operand or P + (-P)),
+//     storing the running product before d_i; the CTA's 128 thread products are combined by shuffles into
+//     F_t (the product of the OTHER threads) and the CTA total T_c.  k_fp_batch_inverse: all T_c of the round
+//     inverted with ONE inversion - a binary extended GCD on the integer-add pipe by a single lane.
+//     k_msm_affine_back: 1 / (thread product) = F_t / T_c; the thread walks back, 1 / d_i = (running inverse)
+//     x (stored prefix), and finishes each addition (operands of the next pair staged by cp.async):
+//     5M + 1S + ~0.4M of sharing per addition, 32 % fewer multiply instructions than XYZZ - and ~500 bytes
+//     of memory traffic per pair against 96 per XYZZ addition, which is why it does not win.
 // ---------------------------------------------------------------------------------------------
 static constexpr int kAffK = 64;         // input positions per thread
 static constexpr int kAffThreads = 128;  // 4096 pairs share one inversion
@@ -1143,7 +1145,7 @@ struct MsmTail {
   size_t words_per_entry() const { return (size_t)(plan.ndig + 1) * 48; }  // 32-bit words of one batch entry
 };
 
-// PB200_MSM_AFFINE=1: bucket accumulation by batched affine additions (k_msm_affine_round) instead of XYZZ
+// PB200_MSM_AFFINE=1: bucket accumulation by batched affine additions (k_msm_affine_fwd / _back) instead of XYZZ
 static bool msm_affine_enabled() {
   static const bool on = [] {
     const char* e = getenv("PB200_MSM_AFFINE");
@@ -1262,7 +1264,7 @@ static int msm_enqueue(const pb200_srs* srs, size_t first, const uint64_t* d_sca
             srs->n_points, first, sorted);
   if (prof_ev) PB_CUDA(cudaEventRecord(prof_ev[0], st));
   if (affine) {
-    // batched-affine pairwise rounds (see k_msm_affine_round)
+    // batched-affine pairwise rounds (see k_msm_affine_fwd)
     const size_t capA = cap / 2 + nb + 2, capB = cap / 4 + nb + 2;
     int rounds = 0;
     while (((size_t)1 << rounds) < cap) rounds++;  // a bucket can hold every entry (equal scalars with equal digits)
