@@ -298,6 +298,42 @@ def test_msm_repeated_scalar_block_is_skewed_but_exact(pb):
     assert R.g1_from_raw_bytes(got.raw) == R.g1_mul(R.g1_mul(R.G1_GEN, gs), R.poly_eval(block, x) * geo % R.R_MOD)
 
 
+def test_commit_key_window_and_sharded_key_on_one_rank(pb):
+    """pb200_srs_upload_window (the ranks of a point-sharded MSM must agree on one window width) gives the same
+    commitments whatever the width, and plonk_b200.dist.ShardedCommitKey degenerates to a plain commit on one rank
+    (device-resident scalars; the replica below the threshold, the slice above it)."""
+    import torch
+
+    from plonk_b200 import dist as pd
+    from plonk_b200._lib import check, lib
+
+    L = lib()
+    rng = random.Random(44)
+    n = 3000
+    pts = progression_bases(n, rng.randrange(1, R.R_MOD), rng.randrange(1, R.R_MOD))
+    raw = bases_to_abi(pts)
+    scalars = rand_fr(rng, n)
+    want = R.g1_to_raw_bytes(R.jac_to_affine(R.msm_pippenger(pts, scalars)))
+    assert L.pb200_msm_window_for(n) == 11 and L.pb200_msm_window_for(1 << 20) == 20
+    for c in (0, 7, 11, 13):
+        h = ctypes.c_void_p()
+        check(L.pb200_srs_upload_window(raw, n, c, ctypes.byref(h)))
+        assert L.pb200_srs_window(h) == (c or 11)
+        out = ctypes.create_string_buffer(96)
+        check(L.pb200_msm_g1(h, to_abi(scalars), n, 1, n, out))
+        assert out.raw == want, c
+        L.pb200_srs_free(h)
+    h = ctypes.c_void_p()
+    assert L.pb200_srs_upload_window(raw, n, 21, ctypes.byref(h)) == -4 and L.pb200_srs_upload_window(raw, n, 1, ctypes.byref(h)) == -4
+    d_sc = torch.frombuffer(bytearray(to_abi(scalars)), dtype=torch.uint8).cuda()
+    for threshold in (1 << 18, 1000):  # replica path, slice path
+        key = pd.ShardedCommitKey(raw, n, None, threshold=threshold, replica_raw=raw[: 96 * min(n, threshold)])
+        assert not key.uses_collective(n)
+        assert key.commit_dev(d_sc.data_ptr(), n) == want
+        assert key.commit_dev(d_sc.data_ptr(), 500) == R.g1_to_raw_bytes(R.jac_to_affine(R.msm_pippenger(pts[:500], scalars[:500])))
+        key.free()
+
+
 def test_msm_skewed_scalars_heavy_buckets(pb):
     """Scalar distributions that put thousands of points into one bucket (the reference's rayon path
     has no such cliff; ours routes buckets longer than 512 entries to whole CTAs)."""

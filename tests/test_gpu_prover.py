@@ -183,6 +183,21 @@ def test_gpu_prover_rejects_bad_arguments(pb):
     # public input position outside the circuit
     bad_idx = (10**6).to_bytes(8, "little") + arrays.pi_idx[8:]
     assert lib().pb200_prove(gpu._h, arrays.witnesses, arrays.n_witnesses, bad_idx, arrays.pi_vals, arrays.n_pi, bl, out) == -4
+    # public inputs announced but not given; positions not strictly increasing (the reference keeps them in a BTreeMap)
+    assert arrays.n_pi >= 2
+    assert lib().pb200_prove(gpu._h, arrays.witnesses, arrays.n_witnesses, None, arrays.pi_vals, arrays.n_pi, bl, out) == -4
+    assert lib().pb200_prove(gpu._h, arrays.witnesses, arrays.n_witnesses, arrays.pi_idx, None, arrays.n_pi, bl, out) == -4
+    dup_idx = arrays.pi_idx[:8] + arrays.pi_idx[:8] + arrays.pi_idx[16:]
+    assert lib().pb200_prove(gpu._h, arrays.witnesses, arrays.n_witnesses, dup_idx, arrays.pi_vals, arrays.n_pi, bl, out) == -4
+    swapped = arrays.pi_idx[8:16] + arrays.pi_idx[:8] + arrays.pi_idx[16:]
+    assert lib().pb200_prove(gpu._h, arrays.witnesses, arrays.n_witnesses, swapped, arrays.pi_vals, arrays.n_pi, bl, out) == -4
+    # device-resident witnesses: the table length is checked too
+    import torch
+
+    d_wit = torch.frombuffer(bytearray(arrays.witnesses), dtype=torch.uint8).cuda()
+    assert lib().pb200_prove_dev(gpu._h, d_wit.data_ptr(), arrays.n_witnesses + 1, arrays.pi_idx, arrays.pi_vals, arrays.n_pi, bl, out, None) == -4
+    assert lib().pb200_prove_dev(gpu._h, d_wit.data_ptr(), arrays.n_witnesses, arrays.pi_idx, arrays.pi_vals, arrays.n_pi, bl, out, None) == 0
+    assert out.raw == gpu.prove(arrays.witnesses, arrays.pi_idx, arrays.pi_vals, bl)
 
 
 def test_gpu_prover_2_20_gates_matches_cpu_oracle(pb):
