@@ -221,7 +221,9 @@ int pb200_srs_upload_window(const uint8_t* raw_points, size_t n_points, int wind
 int pb200_srs_window(const pb200_srs_t* srs) { return srs ? srs_window(srs) : 0; }
 int pb200_msm_window_for(size_t n_points) { return msm_window_for(n_points); }
 void pb200_srs_free(pb200_srs_t* srs) {
-  if (srs) srs_free(srs);
+  if (!srs) return;
+  ensure_init();  // a thread that has made no other pb200 call yet must free on the library's device
+  srs_free(srs);
 }
 size_t pb200_srs_len(const pb200_srs_t* srs) { return srs ? srs_len(srs) : 0; }
 

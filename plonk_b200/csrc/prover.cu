@@ -1394,7 +1394,11 @@ int pb200_prover_from_bytes(const uint8_t* bytes, size_t len, const uint32_t* wi
   return prover_from_bytes(bytes, len, wires, n_witnesses, out);
 }
 
-void pb200_prover_free(pb200_prover_t* p) { prover_free(p); }
+void pb200_prover_free(pb200_prover_t* p) {
+  if (!p) return;
+  ensure_init();  // a thread that has made no other pb200 call yet must free on the library's device
+  prover_free(p);
+}
 
 int pb200_prover_commitments(const pb200_prover_t* p, uint8_t* out /* 15 x 48 */) {
   if (!p || !out) return fail(PB200_ERR_INVALID_ARG, "null argument");
