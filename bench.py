@@ -309,7 +309,9 @@ def run_ours(args):
         "sparse_msm": {"launches": sp_launches.value, "avg_launch_ms": sp_ms.value / max(1, sp_launches.value),
                        "adds_per_launch": sp_adds.value / max(1, sp_launches.value), "points_per_launch": sp_points.value / max(1, sp_launches.value),
                        "share_of_step": (sp_ms.value / 3) / single_ms if single_ms else None},
-        "measured": "3 proofs issued one at a time after the timed region (exclusive kernel durations, CUDA events on the launching stream)",
+        "measured": "3 proofs issued one at a time after the timed region (exclusive kernel durations, CUDA events on the launching stream); "
+                    "a proof that is alone splits its buckets over 2-4 lanes for latency, so these launches do ~25 % more additions than "
+                    "the ones inside the timed region (12 in flight: one lane per bucket)",
         "single_stream_ms_per_proof": single_ms,
         "carry_chain_ceiling": {"fp_products_per_s": fp_peak.value, "adds_per_s": fp_peak.value / FP_PRODUCTS_PER_ADD,
                                 "frac": adds_per_s * FP_PRODUCTS_PER_ADD / fp_peak.value if fp_peak.value else None,

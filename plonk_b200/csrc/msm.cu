@@ -1134,6 +1134,10 @@ static void xyzz_dev_to_host(const uint32_t* w, pbh::HXyzz* o) {
   memcpy(o->zzz.v, w + 36, 48);
 }
 
+// Set by a caller that keeps several MSMs in flight on other streams (prover.cu): dense MSMs then use one lane
+// per bucket (no merge additions).  Thread-local: an MSM is enqueued by the thread that owns its stream.
+thread_local int t_msm_throughput_hint = 0;
+
 // What the host needs to finish an MSM whose kernels have been enqueued: the digit plan of the bucket
 // reduction.  It depends on the window width of the key only, never on the number of scalars, so the
 // ranks of a point-sharded MSM (pb200_msm_g1_allgather*) share it as long as their slices use the same c.
@@ -1222,13 +1226,17 @@ static int msm_enqueue(const pb200_srs* srs, size_t first, const uint64_t* d_sca
     return 0;
   }
 
-  // threads per bucket: enough CTAs to fill the machine, but at least ~8 points per thread
+  // threads per bucket: enough CTAs to fill the machine, but at least ~8 points per thread.  Splitting a bucket
+  // over 2^k lanes costs k full additions per bucket for the merge (+39 % work at k = 2 with 32 entries per
+  // bucket): it buys latency when the launch is alone on the GPU and only costs throughput when other proofs
+  // keep the machine busy - the caller says which (t_msm_throughput_hint, set by the prover from its number of
+  // proofs in flight).
   int log_split = 0;
-  {
+  if (!t_msm_throughput_hint) {
     const size_t avg = cap / nb;
     while (log_split < 5 && ((size_t)nb * batch << log_split) < (1u << 17) && (avg >> (log_split + 1)) >= 8) log_split++;
-    if (const char* env = getenv("PB200_MSM_LOG_SPLIT")) log_split = atoi(env);
   }
+  if (const char* env = getenv("PB200_MSM_LOG_SPLIT")) log_split = atoi(env);
 
   unsigned *counts = nullptr, *offsets = nullptr, *order = nullptr, *ebkt = nullptr, *epos = nullptr, *sorted = nullptr;
   uint4 *sums = nullptr, *classes = nullptr, *S = nullptr, *A = nullptr;

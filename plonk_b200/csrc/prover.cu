@@ -40,6 +40,7 @@ size_t srs_len(const pb200_srs* s);
 const uint4* srs_points(const pb200_srs* s);
 int srs_from_device(const uint4* d_points, size_t n_points, pb200_srs** out, int window_bits);
 int msm_window_for(size_t n_points);
+extern thread_local int t_msm_throughput_hint;
 int g1_check_raw(const uint8_t* raw, size_t n);
 int raw_commit_key_parse(const uint8_t* bytes, size_t len, int checked, size_t* n_points, uint8_t* out_raw);
 int lagrange_key_dev(const uint4* d_in, int log_n, uint4* d_out, cudaStream_t st);
@@ -620,6 +621,7 @@ struct pb200_prover {
   mutable std::vector<pb::Arena> ws_free;
   mutable std::vector<char*> ws_all;
   size_t ws_bytes = 0;
+  mutable std::atomic<int> active{0};  // proofs in flight on this prover (all host threads)
 };
 
 namespace pb {
@@ -979,6 +981,19 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
               const uint64_t* blinders_host, uint8_t* out_proof, cudaStream_t st) {
   const size_t n = P->n, n8 = P->n8, stride = n + 8;
   const int log_n = P->log_n;
+  // With several proofs in flight the dense MSMs give up their latency-oriented bucket splitting (msm.cu)
+  struct InFlight {
+    const pb200_prover* P;
+    explicit InFlight(const pb200_prover* p) : P(p) { P->active.fetch_add(1, std::memory_order_relaxed); }
+    ~InFlight() {
+      P->active.fetch_sub(1, std::memory_order_relaxed);
+      t_msm_throughput_hint = 0;
+    }
+  } in_flight(P);
+  static const int hint_at = [] {  // PB200_THROUGHPUT_AT=<k>: proofs in flight from which the hint is given (0 = never)
+    const char* e = getenv("PB200_THROUGHPUT_AT");
+    return e ? atoi(e) : 2;  // measured on BenchCircuit<2^16>, 12 in flight: never 193.5, from 4: 204.9, from 2: 208.7 proofs/s
+  }();
   const HFr* BL = (const HFr*)blinders_host;
   pbh::Transcript tr = base_transcript(P);
   const HFr* PIV = (const HFr*)pi_vals;
@@ -1075,8 +1090,10 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
     for (int p = 0; p < 4; p++)
       for (int i = 0; i < 2; i++) ba.b[p][i] = to_dev(BL[2 * p + i]);
     PB_LAUNCH(k_lagrange_tail, 1, 32, 0, st, sc, stride, n, ba);
+    t_msm_throughput_hint = 0;  // sparse scalars: long buckets want their lanes
     PB_TRY(msm_run(P->srs_lag, 0, (const uint64_t*)sc, n + 4, 4, stride, aff, st, ar));
   } else {
+    t_msm_throughput_hint = (hint_at > 0 && P->active.load(std::memory_order_relaxed) >= hint_at) ? 1 : 0;
     PB_TRY(msm_run(P->srs, 0, (const uint64_t*)wp, n + 2, 4, stride, aff, st, ar));
   }
   for (int k = 0; k < 4; k++) compress_affine(aff + 12 * k, c48[k]);
@@ -1100,6 +1117,7 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
     for (int i = 0; i < 3; i++) ba.b[0][i] = to_dev(BL[8 + i]);
     PB_LAUNCH(k_blind, 1, 32, 0, st, zp, stride, n, ba);
   }
+  t_msm_throughput_hint = (hint_at > 0 && P->active.load(std::memory_order_relaxed) >= hint_at) ? 1 : 0;
   PB_TRY(msm_run(P->srs, 0, (const uint64_t*)zp, n + 3, 1, stride, aff, st, ar));
   compress_affine(aff, c48[4]);
   tr.append_commitment("z_comm", c48[4]);
@@ -1210,6 +1228,7 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
   PB_LAUNCH(k_split_quotient, dim3(div_up(stride, 256), 4), 256, 0, st, (const uint4*)tcoef, n, t_len, stride, to_dev(BL[11]), to_dev(BL[12]), to_dev(BL[13]), tq);
   const size_t key_len = srs_len(P->srs);
   const size_t tlen = std::min(stride, key_len);
+  t_msm_throughput_hint = (hint_at > 0 && P->active.load(std::memory_order_relaxed) >= hint_at) ? 1 : 0;
   PB_TRY(msm_run(P->srs, 0, (const uint64_t*)tq, tlen, 4, stride, aff, st, ar));  // synchronises the stream
   if (h_flag) return fail(PB200_ERR_UNSATISFIED, "CircuitUnsatisfied");
   for (int k = 0; k < 4; k++) compress_affine(aff + 12 * k, c48[5 + k]);
@@ -1361,6 +1380,7 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
       PB_LAUNCH(k_mul_pointwise, div_up(stride, 128), 128, 0, st, (const uint4*)c_w, (const uint4*)pw_w, stride, c_w);
     }
     const size_t wlen = std::min(stride, key_len);
+    t_msm_throughput_hint = (hint_at > 0 && P->active.load(std::memory_order_relaxed) >= hint_at) ? 1 : 0;
     PB_TRY(msm_run(P->srs, 0, (const uint64_t*)agg, wlen, 2, stride, aff, st, ar));
     compress_affine(aff, c48[9]);
     compress_affine(aff + 12, c48[10]);
