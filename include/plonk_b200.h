@@ -218,6 +218,11 @@ int pb200_prove_dev(const pb200_prover_t* prover, const uint64_t* d_witnesses, s
  * the counters; read returns the summed time, the G1 mixed additions executed (one per non-zero window
  * digit), the launch count and the MSM points processed. */
 int pb200_profile_enable(int on);
+/* The prover gives its dense MSMs one lane per bucket (no merge additions) as soon as two proofs are in flight on
+ * it, and splits buckets over lanes for a proof that is alone (latency).  pb200_throughput_mode(1) makes single
+ * proofs use the in-flight launch shape too, so that a kernel can be timed alone in the shape it has under load;
+ * pb200_throughput_mode(0) restores the automatic choice.  Results never depend on it. */
+int pb200_throughput_mode(int on);
 int pb200_profile_read(double* accumulate_ms, uint64_t* accumulate_adds, uint64_t* accumulate_launches,
                        uint64_t* msm_points);
 /* pb200_profile_read counts the DENSE MSMs (at least a quarter of the window digits non-zero: polynomial

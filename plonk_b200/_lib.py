@@ -27,7 +27,7 @@ EXPORTS = [
     "pb200_srs_upload", "pb200_srs_upload_window", "pb200_msm_window_for", "pb200_srs_window", "pb200_srs_free", "pb200_srs_len",
     "pb200_msm_g1", "pb200_msm_g1_dev", "pb200_msm_g1_range", "pb200_msm_g1_allgather", "pb200_msm_g1_allgather_dev", "pb200_msm_combine_parts",
     "pb200_g1_compress", "pb200_g1_decompress", "pb200_raw_commit_key_points", "pb200_commit_key_from_raw_var_bytes", "pb200_g1_add_affine", "pb200_srs_setup_from_secret", "pb200_g1_lagrange_key",
-    "pb200_profile_enable", "pb200_profile_read", "pb200_profile_read_sparse",
+    "pb200_profile_enable", "pb200_throughput_mode", "pb200_profile_read", "pb200_profile_read_sparse",
     "pb200_prover_new", "pb200_prover_from_bytes", "pb200_prover_free", "pb200_prover_commitments", "pb200_prove", "pb200_prove_dev",
     "pb200_imad_peak", "pb200_fp_product_peak", "pb200_selftest_fr_mul", "pb200_selftest_fp_mul", "pb200_selftest_fp_ops",
 ]
@@ -102,6 +102,7 @@ def lib() -> ctypes.CDLL:
         L.pb200_prove_dev.argtypes = [c.c_void_p, c.c_void_p, c.c_size_t, c.c_void_p, c.c_void_p, c.c_size_t, c.c_void_p, c.c_void_p, c.c_void_p]
         L.pb200_srs_setup_from_secret.argtypes = [c.c_void_p, c.c_void_p, c.c_size_t, c.c_void_p]
         L.pb200_profile_enable.argtypes = [c.c_int]
+        L.pb200_throughput_mode.argtypes = [c.c_int]
         L.pb200_profile_read.argtypes = [c.POINTER(c.c_double), c.POINTER(c.c_uint64), c.POINTER(c.c_uint64), c.POINTER(c.c_uint64)]
         L.pb200_profile_read_sparse.argtypes = L.pb200_profile_read.argtypes
         L.pb200_imad_peak.argtypes = [c.POINTER(c.c_double)]

@@ -41,6 +41,9 @@ const uint4* srs_points(const pb200_srs* s);
 int srs_from_device(const uint4* d_points, size_t n_points, pb200_srs** out, int window_bits);
 int msm_window_for(size_t n_points);
 extern thread_local int t_msm_throughput_hint;
+// pb200_throughput_mode(1): treat every proof as one of many in flight (a measurement aid: bench.py times the
+// dominant kernel with single proofs but wants the launch shape of its timed region)
+static std::atomic<int> g_force_throughput{0};
 int g1_check_raw(const uint8_t* raw, size_t n);
 int raw_commit_key_parse(const uint8_t* bytes, size_t len, int checked, size_t* n_points, uint8_t* out_raw);
 int lagrange_key_dev(const uint4* d_in, int log_n, uint4* d_out, cudaStream_t st);
@@ -1093,7 +1096,7 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
     t_msm_throughput_hint = 0;  // sparse scalars: long buckets want their lanes
     PB_TRY(msm_run(P->srs_lag, 0, (const uint64_t*)sc, n + 4, 4, stride, aff, st, ar));
   } else {
-    t_msm_throughput_hint = (hint_at > 0 && P->active.load(std::memory_order_relaxed) >= hint_at) ? 1 : 0;
+    t_msm_throughput_hint = (hint_at > 0 && (g_force_throughput.load(std::memory_order_relaxed) || P->active.load(std::memory_order_relaxed) >= hint_at)) ? 1 : 0;
     PB_TRY(msm_run(P->srs, 0, (const uint64_t*)wp, n + 2, 4, stride, aff, st, ar));
   }
   for (int k = 0; k < 4; k++) compress_affine(aff + 12 * k, c48[k]);
@@ -1117,7 +1120,7 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
     for (int i = 0; i < 3; i++) ba.b[0][i] = to_dev(BL[8 + i]);
     PB_LAUNCH(k_blind, 1, 32, 0, st, zp, stride, n, ba);
   }
-  t_msm_throughput_hint = (hint_at > 0 && P->active.load(std::memory_order_relaxed) >= hint_at) ? 1 : 0;
+  t_msm_throughput_hint = (hint_at > 0 && (g_force_throughput.load(std::memory_order_relaxed) || P->active.load(std::memory_order_relaxed) >= hint_at)) ? 1 : 0;
   PB_TRY(msm_run(P->srs, 0, (const uint64_t*)zp, n + 3, 1, stride, aff, st, ar));
   compress_affine(aff, c48[4]);
   tr.append_commitment("z_comm", c48[4]);
@@ -1228,7 +1231,7 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
   PB_LAUNCH(k_split_quotient, dim3(div_up(stride, 256), 4), 256, 0, st, (const uint4*)tcoef, n, t_len, stride, to_dev(BL[11]), to_dev(BL[12]), to_dev(BL[13]), tq);
   const size_t key_len = srs_len(P->srs);
   const size_t tlen = std::min(stride, key_len);
-  t_msm_throughput_hint = (hint_at > 0 && P->active.load(std::memory_order_relaxed) >= hint_at) ? 1 : 0;
+  t_msm_throughput_hint = (hint_at > 0 && (g_force_throughput.load(std::memory_order_relaxed) || P->active.load(std::memory_order_relaxed) >= hint_at)) ? 1 : 0;
   PB_TRY(msm_run(P->srs, 0, (const uint64_t*)tq, tlen, 4, stride, aff, st, ar));  // synchronises the stream
   if (h_flag) return fail(PB200_ERR_UNSATISFIED, "CircuitUnsatisfied");
   for (int k = 0; k < 4; k++) compress_affine(aff + 12 * k, c48[5 + k]);
@@ -1380,7 +1383,7 @@ int prove_dev(const pb200_prover* P, const uint64_t* d_wit, const uint64_t* pi_i
       PB_LAUNCH(k_mul_pointwise, div_up(stride, 128), 128, 0, st, (const uint4*)c_w, (const uint4*)pw_w, stride, c_w);
     }
     const size_t wlen = std::min(stride, key_len);
-    t_msm_throughput_hint = (hint_at > 0 && P->active.load(std::memory_order_relaxed) >= hint_at) ? 1 : 0;
+    t_msm_throughput_hint = (hint_at > 0 && (g_force_throughput.load(std::memory_order_relaxed) || P->active.load(std::memory_order_relaxed) >= hint_at)) ? 1 : 0;
     PB_TRY(msm_run(P->srs, 0, (const uint64_t*)agg, wlen, 2, stride, aff, st, ar));
     compress_affine(aff, c48[9]);
     compress_affine(aff + 12, c48[10]);
@@ -1406,6 +1409,11 @@ int pb200_prover_new(const uint8_t* label, size_t label_len, size_t n_constraint
   PB_TRY(ensure_init());
   if (!selectors || !wires || !srs_raw || !out) return fail(PB200_ERR_INVALID_ARG, "null argument");
   return prover_new(label, label_len, n_constraints, selectors, wires, n_witnesses, srs_raw, n_srs_points, out);
+}
+
+int pb200_throughput_mode(int on) {
+  g_force_throughput.store(on ? 1 : 0, std::memory_order_relaxed);
+  return 0;
 }
 
 int pb200_prover_from_bytes(const uint8_t* bytes, size_t len, const uint32_t* wires, size_t n_witnesses, pb200_prover_t** out) {
