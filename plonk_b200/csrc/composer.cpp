@@ -25,9 +25,11 @@ Fr fr_u64(uint64_t x) {
 
 // q * v for a selector coefficient, which is nearly always 0, 1 or -1
 static inline void add_term(Fr& acc, const Fr& q, const Fr& v) {
-  if (q.is_zero()) return;
+  if (q.is_zero() || v.is_zero()) return;
   if (q == Fr::one())
     acc = acc + v;
+  else if (v == Fr::one())  // bits and booleans: half of a gadget circuit's wire values
+    acc = acc + q;
   else
     acc = acc + q * v;
 }
@@ -275,12 +277,20 @@ void Composer::append_gate(Constraint c) {
   append_custom_gate(c);
 }
 
+// append_gate for a constraint the caller no longer needs: q_arith is set in place
+void Composer::append_gate_inplace(Constraint& c) {
+  c.set(Q_ARITH, Fr::one());
+  append_custom_gate(c);
+}
+
 // Solves q_M a b + q_L a + q_R b + q_O c + q_F d + q_C + PI = 0 for c (composer.rs:298-352)
-bool Composer::append_evaluated_output(Constraint s, Witness* out) {
-  const Fr a = (*this)[s.w[0]], b = (*this)[s.w[1]], d = (*this)[s.w[3]];
+bool Composer::append_evaluated_output(Constraint s, Witness* out) { return evaluated_output_inplace(s, out); }
+
+bool Composer::evaluated_output_inplace(Constraint& s, Witness* out) {
+  const Fr &a = (*this)[s.w[0]], &b = (*this)[s.w[1]], &d = (*this)[s.w[3]];
   Fr x = s.q[Q_C];
   if (s.has_pi) x = x + s.pi;
-  if (!s.q[Q_M].is_zero()) add_term(x, s.q[Q_M], a * b);
+  if (!s.q[Q_M].is_zero() && !a.is_zero() && !b.is_zero()) add_term(x, s.q[Q_M], a == Fr::one() ? b : (b == Fr::one() ? a : a * b));
   add_term(x, s.q[Q_L], a);
   add_term(x, s.q[Q_R], b);
   add_term(x, s.q[Q_F], d);
@@ -296,18 +306,18 @@ bool Composer::append_evaluated_output(Constraint s, Witness* out) {
   else
     c = x * y.inv().neg();
   if (solved) {
-    const Witness w = append_witness(c);
+    const Witness w = append_witness(c);  // may reallocate the witness table: a, b, d are not used past this point
     s.c(w);
     if (out) *out = w;
   }
-  append_gate(s);
+  append_gate_inplace(s);
   return solved;
 }
 
 Witness Composer::gate_add(Constraint c) {
   c.set(Q_O, minus_one());
   Witness out = 0;
-  append_evaluated_output(c, &out);
+  evaluated_output_inplace(c, &out);
   return out;
 }
 

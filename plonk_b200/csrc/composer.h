@@ -159,6 +159,8 @@ class Composer {
   std::vector<Fr> witnesses_;
   std::map<size_t, Fr> public_inputs_;
 
+  void append_gate_inplace(Constraint& c);
+  bool evaluated_output_inplace(Constraint& c, Witness* out);
   Witness logic_component(Witness a, Witness b, unsigned bit_pairs, bool is_xor);
   void range_check(Witness value, unsigned num_bits);
   void range_check_even(Witness value, unsigned num_bits);
