@@ -29,3 +29,12 @@ def test_lagrange_basis_wire_commitments_equal_commit_of_blinded_polynomials():
     spec.loader.exec_module(m)
     m.check(16, 3)
     m.check(8, 5)
+
+
+def test_batched_affine_tree_layouts_and_work_split():
+    """tests/models/affine_tree_model.py: the position-based work split and the halving layouts of the opt-in
+    batched-affine bucket accumulation stay inside their buffers and add every bucket exactly once."""
+    spec = importlib.util.spec_from_file_location("affine_tree_model", os.path.join(HERE, "models", "affine_tree_model.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    m.check()
