@@ -71,7 +71,7 @@ Fr fr_recompose(const uint8_t bits[256], int start, int end) {
 const uint64_t kJubJubOrder[4] = {0xd0970e5ed6f72cb7ull, 0xa6682093ccc81082ull, 0x06673b0101343b00ull, 0x0e7db4ea6533afa9ull};
 
 const Fr& edwards_d() {
-  static const Fr d = (fr_u64(10240) * fr_u64(10241).inv()).neg();
+  static const Fr d = (fr_u64(10240) * fr_u64(10241).inv_bingcd()).neg();
   return d;
 }
 
@@ -89,7 +89,7 @@ JubJubAffine jj_add(const JubJubAffine& p, const JubJubAffine& q) {
   const Fr dx = Fr::one() + t, dy = Fr::one() - t;
   // a vanishing denominator is the reference's `sum.get_z() == 0` case (point.rs:226-231)
   if (dx.is_zero() || dy.is_zero()) return jj_identity();
-  const Fr inv = (dx * dy).inv();
+  const Fr inv = (dx * dy).inv_bingcd();
   return {(x1y2 + y1x2) * (inv * dy), (p.v * q.v + p.u * q.u) * (inv * dx)};
 }
 
@@ -135,7 +135,7 @@ static void ext_batch_to_affine(const std::vector<JubJubExt>& in, std::vector<Ju
     pre[i] = acc;
     acc = acc * in[i].z;
   }
-  Fr inv = acc.inv();
+  Fr inv = acc.inv_bingcd();
   for (size_t i = n; i-- > 0;) {
     const Fr zi = inv * pre[i];
     inv = inv * in[i].z;
@@ -304,7 +304,7 @@ bool Composer::evaluated_output_inplace(Constraint& s, Witness* out) {
   else if (y.is_zero())
     solved = false;
   else
-    c = x * y.inv().neg();
+    c = x * y.inv_bingcd().neg();
   if (solved) {
     const Witness w = append_witness(c);  // may reallocate the witness table: a, b, d are not used past this point
     s.c(w);
@@ -493,7 +493,7 @@ void Composer::assert_canonical_truncation(Witness high, Witness low, unsigned n
   const Fr r_high = fr_recompose(mbits, (int)num_bits, 256);
   const Witness diff = gate_add(Constraint().left(minus_one()).a(high).constant(r_high));
   range_check(diff, high_bits);
-  const Witness inverse = append_witness((*this)[diff].inv());  // inv(0) = 0
+  const Witness inverse = append_witness((*this)[diff].inv_bingcd());  // inv(0) = 0
   const Witness product = gate_mul(Constraint().mult(Fr::one()).a(diff).b(inverse));
   const Witness is_top = gate_add(Constraint().left(minus_one()).a(product).constant(Fr::one()));
   append_gate(Constraint().mult(Fr::one()).a(diff).b(is_top));
