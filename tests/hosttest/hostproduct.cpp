@@ -47,6 +47,22 @@ int hp_fp_inv(const uint64_t a[6], uint64_t out[6]) {
   return 0;
 }
 
+// the binary-GCD inverses (host_field.h: inv_bingcd), as used by the circuit front end
+int hp_fp_inv_bingcd(const uint64_t a[6], uint64_t out[6]) {
+  HFp x;
+  memcpy(x.v, a, 48);
+  HFp r = x.inv_bingcd();
+  memcpy(out, r.v, 48);
+  return 0;
+}
+int hp_fr_inv_bingcd(const uint64_t a[4], uint64_t out[4]) {
+  HFr x;
+  memcpy(x.v, a, 32);
+  HFr r = x.inv_bingcd();
+  memcpy(out, r.v, 32);
+  return 0;
+}
+
 int hp_g1_compress(const uint64_t raw[12], uint8_t out[48]) {
   g1_compress_raw(raw, out);
   return 0;

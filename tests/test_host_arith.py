@@ -200,3 +200,12 @@ def test_product_host_field_and_compression(hp):
         out = ctypes.create_string_buffer(48)
         hp.hp_g1_compress(R.g1_to_raw_bytes(p), out)
         assert out.raw == R.g1_compress(p)
+    # binary-GCD inverses: edge values (1, 2, p - 1, powers of two, values with long runs of zero bits) and random ones
+    for mod, nb, fn in ((R.P_MOD, 48, hp.hp_fp_inv_bingcd), (R.R_MOD, 32, hp.hp_fr_inv_bingcd)):
+        mont = 1 << (8 * nb)
+        vals = [1, 2, 3, mod - 1, mod - 2, (mod - 1) // 2, 1 << 64, 1 << 200, (1 << 250) - 1, 0] + [rng.randrange(1, mod) for _ in range(300)]
+        for x in vals:
+            out = (ctypes.c_uint64 * (nb // 8))()
+            fn((x * mont % mod).to_bytes(nb, "little"), out)
+            want = pow(x, -1, mod) * mont % mod if x else 0
+            assert int.from_bytes(bytes(out), "little") == want, (nb, x)
