@@ -150,16 +150,6 @@ def test_ntt_large_properties(pb, log_n):
     v2 = to_abi(rand_fr(rng, 40))
     outs = dom.batch([xb, v2], 0, 1)
     assert outs[0] == ev and outs[1] == dom.coset_fft(v2)
-    # full vectors against the C++ restatement of the reference's schedule (bit-reversal + DIT stages, itself equal
-    # to the Python oracle on every size it reaches, tests/test_cref.py): all four directions, a zero-padded input
-    # (the coset transform of n/8 + 3 coefficients, as in round 3 of the prover) and complete ones
-    from oracle import cref
-
-    assert ev == cref.ntt(xb, log_n, 0, 1)
-    assert back == cref.ntt(ev, log_n, 1, 1)
-    assert dom.fft(ev) == cref.ntt(ev, log_n, 0, 0)
-    assert dom.ifft(ev) == cref.ntt(ev, log_n, 1, 0)
-    assert dom.coset_fft(ev) == cref.ntt(ev, log_n, 0, 1)
 
 
 def _check_msm(pb, pts, scalars_list):
